@@ -1,0 +1,581 @@
+// cfs_cuda.cu -- implementation of the C ABI declared in include/cfs_cuda.h.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "cfs_gen.h"
+#include "common.cuh"
+
+namespace cfsb {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e),
+            what, file, line);
+  cudaGetLastError(); // clear the sticky non-fatal error state
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+    return CFS_ERR_NO_DEVICE;
+  return CFS_ERR_CUDA;
+}
+
+static int g_device = -1;
+
+static int require_device() {
+  if (g_device >= 0) {
+    CFS_CUDA_TRY(cudaSetDevice(g_device));
+    return CFS_OK;
+  }
+  return cfs_cuda_init(0);
+}
+
+enum PtrKind { kPtrHost, kPtrDevice };
+
+static int classify(const void *p, PtrKind *kind) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *kind = kPtrHost;
+    return CFS_OK;
+  }
+  *kind = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)
+              ? kPtrDevice
+              : kPtrHost;
+  return CFS_OK;
+}
+
+// pinned allocations handed out by cfs_cuda_host_alloc (to pick the right free)
+static std::mutex g_alloc_mutex;
+static std::unordered_map<void *, int> g_allocs; // ptr -> 1 pinned, 0 malloc
+
+static int upload_or_borrow(const void *src, size_t bytes, DevArray<char> &own,
+                            const void **out) {
+  PtrKind k;
+  CFS_TRY(classify(src, &k));
+  if (k == kPtrDevice) {
+    *out = src;
+    return CFS_OK;
+  }
+  CFS_TRY(own.alloc(bytes));
+  CFS_CUDA_TRY(cudaMemcpy(own.p, src, bytes, cudaMemcpyHostToDevice));
+  *out = own.p;
+  return CFS_OK;
+}
+
+} // namespace cfsb
+
+using namespace cfsb;
+
+extern "C" {
+
+const char *cfs_cuda_last_error(void) { return g_error; }
+const char *cfs_cuda_version(void) { return "cfs-b200 0.1 (sm_100a)"; }
+
+int cfs_cuda_device_count(int *count) {
+  if (!count)
+    return CFS_ERR_INVALID;
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+  }
+  return CFS_OK;
+}
+
+int cfs_cuda_init(int device) {
+  int n = 0;
+  CFS_TRY(cfs_cuda_device_count(&n));
+  if (n == 0) {
+    set_error("no CUDA device visible: the B200 path has no CPU fallback");
+    return CFS_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (0..%d)", device, n - 1);
+    return CFS_ERR_INVALID;
+  }
+  CFS_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CFS_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only",
+              device, prop.major, prop.minor);
+    return CFS_ERR_NO_DEVICE;
+  }
+  g_device = device;
+  return CFS_OK;
+}
+
+void *cfs_cuda_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) {
+    if (g_device >= 0)
+      cudaSetDevice(g_device);
+    if (cudaHostAlloc(&p, bytes ? bytes : 64, cudaHostAllocPortable) ==
+        cudaSuccess) {
+      std::lock_guard<std::mutex> hold(g_alloc_mutex);
+      g_allocs[p] = 1;
+      return p;
+    }
+  }
+  cudaGetLastError();
+  // host-only bookkeeping (MMF loading on a box without a GPU): plain 64-byte
+  // aligned memory, exactly what the reference returns (allocator.cpp:33)
+  if (posix_memalign(&p, 64, bytes ? bytes : 64) != 0)
+    return nullptr;
+  std::lock_guard<std::mutex> hold(g_alloc_mutex);
+  g_allocs[p] = 0;
+  return p;
+}
+
+void cfs_cuda_host_free(void *ptr) {
+  if (!ptr)
+    return;
+  int kind = 0;
+  {
+    std::lock_guard<std::mutex> hold(g_alloc_mutex);
+    auto it = g_allocs.find(ptr);
+    if (it == g_allocs.end()) {
+      free(ptr); // not ours: behave like the reference's free()
+      return;
+    }
+    kind = it->second;
+    g_allocs.erase(it);
+  }
+  if (kind == 1)
+    cudaFreeHost(ptr);
+  else
+    free(ptr);
+}
+
+static int create_common(cfs_mat_t *out, int32_t nrows, int32_t ncols,
+                         int32_t row_begin, int32_t global_nrows, bool sharded,
+                         const int32_t *rowptr, const int32_t *colind,
+                         const void *values, int is_double, int symmetric) {
+  if (!out || !rowptr || nrows < 0 || ncols < 0) {
+    set_error("cfs_cuda_matrix_create: bad arguments");
+    return CFS_ERR_INVALID;
+  }
+  CFS_TRY(require_device());
+  cfs_matrix_s *m = new cfs_matrix_s;
+  m->device = g_device;
+  m->is_double = is_double != 0;
+  m->symmetric = symmetric != 0;
+  m->nrows = nrows;
+  m->ncols = ncols;
+  m->row_begin = row_begin;
+  m->global_nrows = global_nrows;
+  m->sharded = sharded;
+  int status = CFS_OK;
+  do {
+    // rowptr first: its last entry is nnz (csr_matrix.tpp:122)
+    DevArray<char> tmp;
+    const void *p = nullptr;
+    PtrKind k;
+    classify(rowptr, &k);
+    int32_t nnz = 0;
+    if (k == kPtrDevice) {
+      if (cudaMemcpy(&nnz, rowptr + nrows, 4, cudaMemcpyDeviceToHost) !=
+          cudaSuccess) {
+        status = cuda_fail(cudaGetLastError(), "read nnz", __FILE__, __LINE__);
+        break;
+      }
+      m->csr_rowptr = rowptr;
+    } else {
+      nnz = rowptr[nrows];
+      if ((status = m->own_rowptr.alloc((size_t)nrows + 1)) != CFS_OK)
+        break;
+      if (cudaMemcpy(m->own_rowptr.p, rowptr, ((size_t)nrows + 1) * 4,
+                     cudaMemcpyHostToDevice) != cudaSuccess) {
+        status = cuda_fail(cudaGetLastError(), "upload rowptr", __FILE__,
+                           __LINE__);
+        break;
+      }
+      m->csr_rowptr = m->own_rowptr.p;
+    }
+    m->nnz_full = nnz;
+    if (nnz > 0 && (!colind || !values)) {
+      set_error("cfs_cuda_matrix_create: null colind/values");
+      status = CFS_ERR_INVALID;
+      break;
+    }
+    classify(colind, &k);
+    if (k == kPtrDevice || nnz == 0) {
+      m->csr_colind = colind;
+    } else {
+      if ((status = m->own_colind.alloc((size_t)nnz)) != CFS_OK)
+        break;
+      if (cudaMemcpy(m->own_colind.p, colind, (size_t)nnz * 4,
+                     cudaMemcpyHostToDevice) != cudaSuccess) {
+        status = cuda_fail(cudaGetLastError(), "upload colind", __FILE__,
+                           __LINE__);
+        break;
+      }
+      m->csr_colind = m->own_colind.p;
+    }
+    if (nnz == 0)
+      m->csr_values = values;
+    else if ((status = upload_or_borrow(values, (size_t)nnz * m->vsize(),
+                                        m->own_values, &p)) != CFS_OK)
+      break;
+    else
+      m->csr_values = p;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) !=
+        cudaSuccess) {
+      status = cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__,
+                         __LINE__);
+      break;
+    }
+  } while (0);
+  if (status != CFS_OK) {
+    delete m;
+    return status;
+  }
+  *out = m;
+  return CFS_OK;
+}
+
+int cfs_cuda_matrix_create(cfs_mat_t *out, int32_t nrows, int32_t ncols,
+                           const int32_t *rowptr, const int32_t *colind,
+                           const void *values, int is_double, int symmetric) {
+  return create_common(out, nrows, ncols, 0, nrows, false, rowptr, colind,
+                       values, is_double, symmetric);
+}
+
+int cfs_cuda_matrix_create_shard(cfs_mat_t *out, int32_t global_nrows,
+                                 int32_t row_begin, int32_t row_end,
+                                 const int32_t *rowptr, const int32_t *colind,
+                                 const void *values, int is_double) {
+  if (row_begin < 0 || row_end < row_begin || row_end > global_nrows) {
+    set_error("cfs_cuda_matrix_create_shard: bad row range");
+    return CFS_ERR_INVALID;
+  }
+  return create_common(out, row_end - row_begin, global_nrows, row_begin,
+                       global_nrows, true, rowptr, colind, values, is_double,
+                       1);
+}
+
+int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
+  (void)tuning; // Tuning only selects the CPU partitioner for CSR (:250-254)
+  if (!m)
+    return CFS_ERR_INVALID;
+  if (m->tuned) {
+    set_error("cfs_cuda_matrix_tune: matrix already tuned");
+    return CFS_ERR_STATE;
+  }
+  CFS_CUDA_TRY(cudaSetDevice(m->device));
+  if (nparts < 1)
+    nparts = 1;
+  m->nparts = nparts;
+  int meta_status = CFS_OK;
+  if (!m->symmetric) {
+    // plain CSR (cpu_mv): keep a device copy that outlives the caller's arrays
+    if (!m->own_rowptr.p) {
+      CFS_TRY(m->own_rowptr.alloc((size_t)m->nrows + 1));
+      CFS_CUDA_TRY(cudaMemcpy(m->own_rowptr.p, m->csr_rowptr,
+                              ((size_t)m->nrows + 1) * 4,
+                              cudaMemcpyDeviceToDevice));
+      m->csr_rowptr = m->own_rowptr.p;
+    }
+    if (!m->own_colind.p && m->nnz_full) {
+      CFS_TRY(m->own_colind.alloc((size_t)m->nnz_full));
+      CFS_CUDA_TRY(cudaMemcpy(m->own_colind.p, m->csr_colind,
+                              (size_t)m->nnz_full * 4,
+                              cudaMemcpyDeviceToDevice));
+      m->csr_colind = m->own_colind.p;
+    }
+    if (!m->own_values.p && m->nnz_full) {
+      CFS_TRY(m->own_values.alloc((size_t)m->nnz_full * m->vsize()));
+      CFS_CUDA_TRY(cudaMemcpy(m->own_values.p, m->csr_values,
+                              (size_t)m->nnz_full * m->vsize(),
+                              cudaMemcpyDeviceToDevice));
+      m->csr_values = m->own_values.p;
+    }
+  } else {
+    if (!m->sharded && m->nrows != m->ncols) {
+      set_error("symmetric matrix must be square");
+      return CFS_ERR_INVALID;
+    }
+    CFS_TRY(build_lower(m, m->stream));
+    CFS_TRY(build_layout(m, m->stream));
+    // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
+    m->row_split.assign((size_t)nparts + 1, 0);
+    if (nparts > 1) {
+      if (m->sharded) {
+        set_error("reference-compatible metadata (nparts > 1) is defined on "
+                  "the unsharded matrix only");
+        return CFS_ERR_INVALID;
+      }
+      const long long S = ((m->nrows / nparts - 1) | (kBlkFactor - 1)) + 1;
+      if (m->nrows / nparts < 1 || (long long)(nparts - 1) * S > m->nrows) {
+        // the reference overshoots row_split_ and crashes here
+        set_error("nparts=%d is not a valid partition count for %d rows",
+                  nparts, m->nrows);
+        return CFS_ERR_INVALID;
+      }
+      for (int t = 0; t < nparts; ++t)
+        m->row_split[t] = (int32_t)(t * S);
+      m->row_split[nparts] = m->nrows;
+      meta_status = build_refmeta(m, m->stream);
+      if (meta_status != CFS_OK && meta_status != CFS_ERR_TOO_LARGE)
+        return meta_status;
+    } else {
+      m->row_split[1] = m->nrows;
+    }
+    // compress_symmetry() frees the full CSR when it owns it (:1700-1706)
+    m->own_rowptr.release();
+    m->own_colind.release();
+    m->own_values.release();
+    m->csr_rowptr = m->csr_colind = nullptr;
+    m->csr_values = nullptr;
+  }
+  m->tuned = true;
+  return meta_status;
+}
+
+void cfs_cuda_matrix_destroy(cfs_mat_t m) {
+  if (!m)
+    return;
+  cudaSetDevice(m->device);
+  if (m->stream)
+    cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
+  if (!m || !info)
+    return CFS_ERR_INVALID;
+  memset(info, 0, sizeof(*info));
+  const int64_t vs = (int64_t)m->vsize();
+  info->nrows = m->nrows;
+  info->ncols = m->ncols;
+  info->row_begin = m->row_begin;
+  info->halo_begin = m->halo_begin;
+  info->nnz_full = m->nnz_full;
+  info->nnz_low = m->nnz_low;
+  info->nnz_diag = m->nnz_diag;
+  info->nparts = m->nparts;
+  info->ncolors = m->ncolors;
+  info->nranges = m->nranges;
+  info->symmetric = m->symmetric;
+  info->is_double = m->is_double;
+  info->tuned = m->tuned;
+  info->refmeta = m->refmeta;
+  info->nvrows = m->nvrows;
+  info->nslices = m->nslices;
+  info->padded_entries = m->padded_entries;
+  info->nconflict_edges = m->nedges;
+  if (m->symmetric && m->tuned) {
+    // size(), csr_matrix.tpp:191-228 (including its (nrows + 1*nthreads) term)
+    int64_t s = ((int64_t)m->nrows + 1LL * m->nparts) * 4;
+    s += m->nnz_low * 4 + m->nnz_low * vs + m->nnz_diag * vs;
+    if (m->nparts > 1) {
+      s += ((int64_t)m->ncolors + 1) * 4;
+      s += 2LL * m->nranges * 4;
+    }
+    info->size_bytes = s;
+    // SURVEY.md 8(d)
+    info->algorithmic_bytes = m->nnz_low * (vs + 4) + (int64_t)m->nrows * vs +
+                              ((int64_t)m->nrows + 1) * 4 +
+                              2 * (int64_t)m->nrows * vs;
+  } else {
+    info->size_bytes = ((int64_t)m->nrows + 1) * 4 + m->nnz_full * (4 + vs);
+    info->algorithmic_bytes = info->size_bytes + 2 * (int64_t)m->nrows * vs;
+  }
+  info->device_bytes =
+      (int64_t)(m->own_rowptr.bytes() + m->own_colind.bytes() +
+                m->own_values.bytes() + m->low_rowptr.bytes() +
+                m->low_colind.bytes() + m->low_values.bytes() +
+                m->diagonal.bytes() + m->slice_ptr.bytes() +
+                m->vrow_row.bytes() + m->sell_col.bytes() +
+                m->sell_val.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
+                m->adj.bytes() + m->color.bytes() + m->color_first.bytes() +
+                m->range_ptr.bytes() + m->part_nranges.bytes() +
+                m->range_start.bytes() + m->range_end.bytes() +
+                m->stage_x.bytes() + m->stage_y.bytes());
+  return CFS_OK;
+}
+
+int cfs_cuda_spmv_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                        void *stream) {
+  if (!m || !y_dev || !x_dev)
+    return CFS_ERR_INVALID;
+  if (!m->tuned) {
+    set_error("cfs_cuda_spmv: call cfs_cuda_matrix_tune first");
+    return CFS_ERR_STATE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m->symmetric)
+    return launch_sym_spmv(m, y_dev, x_dev, s);
+  return launch_csr_spmv(m, y_dev, x_dev, s);
+}
+
+int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
+  if (!m || !y || !x)
+    return CFS_ERR_INVALID;
+  if (!m->tuned) {
+    set_error("cfs_cuda_spmv: call cfs_cuda_matrix_tune first");
+    return CFS_ERR_STATE;
+  }
+  CFS_CUDA_TRY(cudaSetDevice(m->device));
+  const size_t vs = m->vsize();
+  const size_t xlen = m->sharded
+                          ? (size_t)(m->row_begin + m->nrows - m->halo_begin)
+                          : (size_t)m->ncols;
+  const size_t ylen = m->sharded ? xlen : (size_t)m->nrows;
+  PtrKind kx, ky;
+  classify(x, &kx);
+  classify(y, &ky);
+  const void *xd = x;
+  void *yd = y;
+  if (kx == kPtrHost) {
+    if (!m->stage_x.p)
+      CFS_TRY(m->stage_x.alloc(xlen * vs));
+    CFS_CUDA_TRY(cudaMemcpyAsync(m->stage_x.p, x, xlen * vs,
+                                 cudaMemcpyHostToDevice, m->stream));
+    xd = m->stage_x.p;
+  }
+  if (ky == kPtrHost) {
+    if (!m->stage_y.p)
+      CFS_TRY(m->stage_y.alloc(ylen * vs));
+    yd = m->stage_y.p;
+  }
+  CFS_TRY(cfs_cuda_spmv_async(m, yd, xd, m->stream));
+  if (ky == kPtrHost)
+    CFS_CUDA_TRY(cudaMemcpyAsync(y, yd, ylen * vs, cudaMemcpyDeviceToHost,
+                                 m->stream));
+  CFS_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return CFS_OK;
+}
+
+// ---- metadata export ------------------------------------------------------
+static int copy_out(const void *dev, size_t n, size_t elem, void *dst,
+                    size_t cap, size_t *count) {
+  if (count)
+    *count = n;
+  if (!dst)
+    return CFS_OK;
+  if (cap < n) {
+    set_error("export buffer too small: need %zu elements", n);
+    return CFS_ERR_INVALID;
+  }
+  if (n)
+    CFS_CUDA_TRY(cudaMemcpy(dst, dev, n * elem, cudaMemcpyDeviceToHost));
+  return CFS_OK;
+}
+
+int cfs_cuda_matrix_export(cfs_mat_t m, int what, void *dst, size_t cap,
+                           size_t *count) {
+  if (!m || !m->tuned || !m->symmetric) {
+    set_error("cfs_cuda_matrix_export: needs a tuned symmetric matrix");
+    return CFS_ERR_STATE;
+  }
+  CFS_CUDA_TRY(cudaSetDevice(m->device));
+  const size_t vs = m->vsize();
+  const int P = m->nparts;
+  const size_t N = (size_t)m->nrows;
+  switch (what) {
+  case CFS_META_ROW_SPLIT: {
+    const size_t n = (size_t)P + 1;
+    if (count)
+      *count = n;
+    if (dst) {
+      if (cap < n)
+        return CFS_ERR_INVALID;
+      memcpy(dst, m->row_split.data(), n * 4);
+    }
+    return CFS_OK;
+  }
+  case CFS_META_PART_NNZ_LOW:
+  case CFS_META_LOWER_ROWPTR: {
+    // per-partition local rowptr_ (csr_matrix.tpp:1233-1234, 1294-1296) from
+    // the global lower rowptr
+    std::vector<int32_t> g(N + 1);
+    if (N + 1)
+      CFS_CUDA_TRY(cudaMemcpy(g.data(), m->low_rowptr.p, (N + 1) * 4,
+                              cudaMemcpyDeviceToHost));
+    std::vector<int32_t> outv;
+    if (what == CFS_META_PART_NNZ_LOW) {
+      for (int t = 0; t < P; ++t)
+        outv.push_back(g[m->row_split[t + 1]] - g[m->row_split[t]]);
+    } else {
+      outv.reserve(N + P);
+      for (int t = 0; t < P; ++t)
+        for (int i = m->row_split[t]; i <= m->row_split[t + 1]; ++i)
+          outv.push_back(g[i] - g[m->row_split[t]]);
+    }
+    if (count)
+      *count = outv.size();
+    if (dst) {
+      if (cap < outv.size())
+        return CFS_ERR_INVALID;
+      memcpy(dst, outv.data(), outv.size() * 4);
+    }
+    return CFS_OK;
+  }
+  case CFS_META_LOWER_COLIND:
+    return copy_out(m->low_colind.p, (size_t)m->nnz_low, 4, dst, cap, count);
+  case CFS_META_LOWER_VALUES:
+    return copy_out(m->low_values.p, (size_t)m->nnz_low, vs, dst, cap, count);
+  case CFS_META_DIAGONAL:
+    return copy_out(m->diagonal.p, N, vs, dst, cap, count);
+  case CFS_META_SELL_SLICE_PTR:
+    return copy_out(m->slice_ptr.p, (size_t)m->nslices + 1, 4, dst, cap, count);
+  case CFS_META_SELL_VROW:
+    return copy_out(m->vrow_row.p, (size_t)m->nslices * kSliceRows, 4, dst, cap,
+                    count);
+  case CFS_META_SELL_COL:
+    return copy_out(m->sell_col.p, (size_t)m->padded_entries, 4, dst, cap,
+                    count);
+  case CFS_META_SELL_VAL:
+    return copy_out(m->sell_val.p, (size_t)m->padded_entries, vs, dst, cap,
+                    count);
+  default:
+    break;
+  }
+  if (!m->refmeta) {
+    // P == 1 (serial(), csr_matrix.tpp:642) has no graph / colours / ranges
+    if (count)
+      *count = 0;
+    return CFS_OK;
+  }
+  const size_t V = (size_t)m->nblk;
+  switch (what) {
+  case CFS_META_WEIGHT:
+    return copy_out(m->weight.p, V, 4, dst, cap, count);
+  case CFS_META_ADJ_PTR:
+    return copy_out(m->adj_ptr.p, V + 1, 4, dst, cap, count);
+  case CFS_META_ADJ:
+    return copy_out(m->adj.p, (size_t)m->nedges, 4, dst, cap, count);
+  case CFS_META_COLOR_FIRST:
+    return copy_out(m->color_first.p, V, 4, dst, cap, count);
+  case CFS_META_COLOR:
+    return copy_out(m->color.p, V, 4, dst, cap, count);
+  case CFS_META_RANGE_PTR:
+    return copy_out(m->range_ptr.p, (size_t)P * (m->ncolors + 1), 4, dst, cap,
+                    count);
+  case CFS_META_PART_NRANGES:
+    return copy_out(m->part_nranges.p, (size_t)P, 4, dst, cap, count);
+  case CFS_META_RANGE_START:
+    return copy_out(m->range_start.p, (size_t)m->nranges, 4, dst, cap, count);
+  case CFS_META_RANGE_END:
+    return copy_out(m->range_end.p, (size_t)m->nranges, 4, dst, cap, count);
+  default:
+    set_error("cfs_cuda_matrix_export: unknown selector %d", what);
+    return CFS_ERR_INVALID;
+  }
+}
+
+} // extern "C"

@@ -1,0 +1,297 @@
+// preproc.cu -- GPU format conversion.
+//
+//   build_lower : full CSR -> lower-triangle CSR + dense diagonal. This is the
+//                 reference's symmetry compression, serial()
+//                 (include/matrix/csr_matrix.tpp:642-706) and the extraction
+//                 loop of conflict_free_aposteriori() (:1257-1292): entries in
+//                 CSR order, col < row kept with GLOBAL column id, col == row
+//                 goes to diagonal_, col > row dropped. Bit-exact by
+//                 construction (pure copies).
+//   build_layout: lower CSR -> the execution layout of the sm_100a kernel:
+//                 rows cut into virtual rows of <= kMaxChunk entries, 32
+//                 virtual rows per slice (one per warp lane), entries stored
+//                 slice-column-major so that every warp load of values /
+//                 indices is one fully coalesced 256 B / 128 B request.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace cfsb {
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(size_t n, int per = kThreads) {
+  return (unsigned)((n + per - 1) / per);
+}
+
+// ---- lower extraction ----------------------------------------------------
+__global__ void count_lower_kernel(int nrows, int row_begin,
+                                   const int *__restrict__ rowptr,
+                                   const int *__restrict__ colind,
+                                   int *__restrict__ low_count,
+                                   int *__restrict__ min_col,
+                                   unsigned long long *__restrict__ ndiag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int my_min = INT_MAX, my_diag = 0;
+  if (i < nrows) {
+    const int grow = row_begin + i;
+    int cnt = 0;
+    for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+      const int c = colind[j];
+      cnt += (c < grow);
+      my_diag += (c == grow);
+      my_min = min(my_min, c);
+    }
+    low_count[i] = cnt;
+  }
+  // block reduce of min column / diagonal count
+  typedef cub::BlockReduce<int, kThreads> Reduce;
+  __shared__ typename Reduce::TempStorage tmp;
+  int bmin = Reduce(tmp).Reduce(my_min, cub::Min());
+  __syncthreads();
+  int bdiag = Reduce(tmp).Sum(my_diag);
+  if (threadIdx.x == 0) {
+    atomicMin(min_col, bmin);
+    atomicAdd(ndiag, (unsigned long long)bdiag);
+  }
+}
+
+template <typename T>
+__global__ void fill_lower_kernel(int nrows, int row_begin,
+                                  const int *__restrict__ rowptr,
+                                  const int *__restrict__ colind,
+                                  const T *__restrict__ values,
+                                  const int *__restrict__ low_rowptr,
+                                  int *__restrict__ low_colind,
+                                  T *__restrict__ low_values,
+                                  T *__restrict__ diagonal) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows)
+    return;
+  const int grow = row_begin + i;
+  int out = low_rowptr[i];
+  T d = 0; // the reference zero-fills diagonal_
+  for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+    const int c = colind[j];
+    if (c < grow) {
+      low_colind[out] = c;
+      low_values[out] = values[j];
+      ++out;
+    } else if (c == grow) {
+      d = values[j]; // last one wins, like the reference's overwrite
+    }
+  }
+  diagonal[i] = d;
+}
+
+// ---- virtual rows ----------------------------------------------------------
+__global__ void count_vrows_kernel(int nrows,
+                                   const int *__restrict__ low_rowptr,
+                                   int *__restrict__ nv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows)
+    return;
+  const int len = low_rowptr[i + 1] - low_rowptr[i];
+  nv[i] = len == 0 ? 1 : (len + kMaxChunk - 1) / kMaxChunk;
+}
+
+__global__ void fill_vrows_kernel(int nrows, int row_begin,
+                                  const int *__restrict__ low_rowptr,
+                                  const int *__restrict__ voff,
+                                  int *__restrict__ vrow_row,
+                                  int *__restrict__ vrow_start,
+                                  int *__restrict__ vrow_len) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows)
+    return;
+  const int begin = low_rowptr[i];
+  const int len = low_rowptr[i + 1] - begin;
+  int v = voff[i];
+  int done = 0, chunk = 0;
+  do {
+    const int take = min(kMaxChunk, len - done);
+    vrow_row[v] = (row_begin + i) | (chunk ? kVrowCont : 0);
+    vrow_start[v] = begin + done;
+    vrow_len[v] = take;
+    done += take;
+    ++v;
+    ++chunk;
+  } while (done < len);
+}
+
+__global__ void slice_width_kernel(long long nvrows, long long nslices,
+                                   const int *__restrict__ vrow_len,
+                                   int *__restrict__ width) {
+  long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  long long v = s * kSliceRows + lane;
+  int len = v < nvrows ? vrow_len[v] : 0;
+  for (int o = 16; o; o >>= 1)
+    len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0)
+    width[s] = len;
+}
+
+template <typename T>
+__global__ void fill_sell_kernel(long long nvrows, long long nslices,
+                                 const int *__restrict__ slice_ptr,
+                                 const int *__restrict__ vrow_start,
+                                 const int *__restrict__ vrow_len,
+                                 const int *__restrict__ low_colind,
+                                 const T *__restrict__ low_values,
+                                 int *__restrict__ vrow_row,
+                                 int *__restrict__ sell_col,
+                                 T *__restrict__ sell_val) {
+  long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  const long long v = s * kSliceRows + lane;
+  int start = 0, len = 0;
+  if (v < nvrows) {
+    start = vrow_start[v];
+    len = vrow_len[v];
+  } else {
+    vrow_row[v] = -1; // inactive lane of the last slice
+  }
+  const int w = slice_ptr[s + 1] - slice_ptr[s];
+  size_t base = (size_t)slice_ptr[s] * kSliceRows + lane;
+  for (int k = 0; k < w; ++k) {
+    int c = -1;
+    T a = 0;
+    if (k < len) {
+      c = low_colind[start + k];
+      a = low_values[start + k];
+    }
+    sell_col[base + (size_t)k * kSliceRows] = c;
+    sell_val[base + (size_t)k * kSliceRows] = a;
+  }
+}
+
+int exclusive_scan_i32(const int *in, int *out, size_t n, cudaStream_t s) {
+  size_t tmp_bytes = 0;
+  CFS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out,
+                                             (long long)n, s));
+  DevArray<char> tmp;
+  CFS_TRY(tmp.alloc(tmp_bytes));
+  CFS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out,
+                                             (long long)n, s));
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  return CFS_OK;
+}
+
+} // namespace
+
+int build_lower(cfs_matrix_s *m, cudaStream_t s) {
+  const int n = m->nrows;
+  DevArray<int> counts; // n+1 so that the scan yields rowptr[n]
+  CFS_TRY(counts.alloc((size_t)n + 1));
+  CFS_CUDA_TRY(cudaMemsetAsync(counts.p, 0, ((size_t)n + 1) * 4, s));
+  DevArray<int> min_col;
+  DevArray<unsigned long long> ndiag;
+  CFS_TRY(min_col.alloc(1));
+  CFS_TRY(ndiag.alloc(1));
+  const int init_min = m->row_begin;
+  CFS_CUDA_TRY(cudaMemcpyAsync(min_col.p, &init_min, 4, cudaMemcpyHostToDevice,
+                               s));
+  CFS_CUDA_TRY(cudaMemsetAsync(ndiag.p, 0, 8, s));
+  if (n > 0)
+    count_lower_kernel<<<blocks_for(n), kThreads, 0, s>>>(
+        n, m->row_begin, m->csr_rowptr, m->csr_colind, counts.p, min_col.p,
+        ndiag.p);
+  CFS_CUDA_TRY(cudaGetLastError());
+  CFS_TRY(m->low_rowptr.alloc((size_t)n + 1));
+  CFS_TRY(exclusive_scan_i32(counts.p, m->low_rowptr.p, (size_t)n + 1, s));
+  int nlow = 0, hmin = 0;
+  unsigned long long hdiag = 0;
+  CFS_CUDA_TRY(cudaMemcpy(&nlow, m->low_rowptr.p + n, 4,
+                          cudaMemcpyDeviceToHost));
+  CFS_CUDA_TRY(cudaMemcpy(&hmin, min_col.p, 4, cudaMemcpyDeviceToHost));
+  CFS_CUDA_TRY(cudaMemcpy(&hdiag, ndiag.p, 8, cudaMemcpyDeviceToHost));
+  m->nnz_low = nlow;
+  m->nnz_diag = (int64_t)hdiag;
+  m->halo_begin = m->sharded ? (hmin < 0 ? 0 : hmin) : 0;
+  CFS_TRY(m->low_colind.alloc((size_t)nlow));
+  CFS_TRY(m->low_values.alloc((size_t)nlow * m->vsize()));
+  CFS_TRY(m->diagonal.alloc((size_t)n * m->vsize()));
+  if (n > 0) {
+    if (m->is_double)
+      fill_lower_kernel<double><<<blocks_for(n), kThreads, 0, s>>>(
+          n, m->row_begin, m->csr_rowptr, m->csr_colind,
+          (const double *)m->csr_values, m->low_rowptr.p, m->low_colind.p,
+          (double *)m->low_values.p, (double *)m->diagonal.p);
+    else
+      fill_lower_kernel<float><<<blocks_for(n), kThreads, 0, s>>>(
+          n, m->row_begin, m->csr_rowptr, m->csr_colind,
+          (const float *)m->csr_values, m->low_rowptr.p, m->low_colind.p,
+          (float *)m->low_values.p, (float *)m->diagonal.p);
+  }
+  CFS_CUDA_TRY(cudaGetLastError());
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  return CFS_OK;
+}
+
+int build_layout(cfs_matrix_s *m, cudaStream_t s) {
+  const int n = m->nrows;
+  // virtual rows
+  DevArray<int> nv, voff;
+  CFS_TRY(nv.alloc((size_t)n + 1));
+  CFS_TRY(voff.alloc((size_t)n + 1));
+  CFS_CUDA_TRY(cudaMemsetAsync(nv.p, 0, ((size_t)n + 1) * 4, s));
+  if (n > 0)
+    count_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(n, m->low_rowptr.p,
+                                                          nv.p);
+  CFS_CUDA_TRY(cudaGetLastError());
+  CFS_TRY(exclusive_scan_i32(nv.p, voff.p, (size_t)n + 1, s));
+  int nvrows = 0;
+  CFS_CUDA_TRY(cudaMemcpy(&nvrows, voff.p + n, 4, cudaMemcpyDeviceToHost));
+  m->nvrows = nvrows;
+  m->nslices = (nvrows + kSliceRows - 1) / kSliceRows;
+  const size_t nlanes = (size_t)m->nslices * kSliceRows;
+  DevArray<int> vstart, vlen;
+  CFS_TRY(m->vrow_row.alloc(nlanes));
+  CFS_TRY(vstart.alloc(nlanes));
+  CFS_TRY(vlen.alloc(nlanes));
+  if (n > 0)
+    fill_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(
+        n, m->row_begin, m->low_rowptr.p, voff.p, m->vrow_row.p, vstart.p,
+        vlen.p);
+  CFS_CUDA_TRY(cudaGetLastError());
+  // slice widths -> slice_ptr
+  DevArray<int> width;
+  CFS_TRY(width.alloc((size_t)m->nslices + 1));
+  CFS_CUDA_TRY(cudaMemsetAsync(width.p, 0, ((size_t)m->nslices + 1) * 4, s));
+  if (m->nslices > 0)
+    slice_width_kernel<<<blocks_for(nlanes), kThreads, 0, s>>>(
+        m->nvrows, m->nslices, vlen.p, width.p);
+  CFS_CUDA_TRY(cudaGetLastError());
+  CFS_TRY(m->slice_ptr.alloc((size_t)m->nslices + 1));
+  CFS_TRY(exclusive_scan_i32(width.p, m->slice_ptr.p, (size_t)m->nslices + 1,
+                             s));
+  int total_width = 0;
+  CFS_CUDA_TRY(cudaMemcpy(&total_width, m->slice_ptr.p + m->nslices, 4,
+                          cudaMemcpyDeviceToHost));
+  m->padded_entries = (int64_t)total_width * kSliceRows;
+  CFS_TRY(m->sell_col.alloc((size_t)m->padded_entries));
+  CFS_TRY(m->sell_val.alloc((size_t)m->padded_entries * m->vsize()));
+  if (m->nslices > 0) {
+    if (m->is_double)
+      fill_sell_kernel<double><<<blocks_for(nlanes), kThreads, 0, s>>>(
+          m->nvrows, m->nslices, m->slice_ptr.p, vstart.p, vlen.p,
+          m->low_colind.p, (const double *)m->low_values.p, m->vrow_row.p,
+          m->sell_col.p, (double *)m->sell_val.p);
+    else
+      fill_sell_kernel<float><<<blocks_for(nlanes), kThreads, 0, s>>>(
+          m->nvrows, m->nslices, m->slice_ptr.p, vstart.p, vlen.p,
+          m->low_colind.p, (const float *)m->low_values.p, m->vrow_row.p,
+          m->sell_col.p, (float *)m->sell_val.p);
+  }
+  CFS_CUDA_TRY(cudaGetLastError());
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  return CFS_OK;
+}
+
+} // namespace cfsb

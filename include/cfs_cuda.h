@@ -1,0 +1,175 @@
+/*
+ * cfs_cuda.h -- the C ABI of the B200 symmetric-SpMV path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * The C++ classes of include/ (SparseMatrix, CSRMatrix, SpDMV -- same names and
+ * signatures as the reference's include/cfs.hpp) are thin callers of these
+ * entry points; a maintainer of the reference would bind exactly these from
+ * csr_matrix.tpp (see INTEGRATION.md for the stub).
+ *
+ * Each entry point names the reference interface it replaces
+ * (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns CFS_OK (0) or a CFS_ERR_* code; the message of the
+ *     last failure on the calling thread is cfs_cuda_last_error().
+ *     The C++ layer maps non-zero to the reference's convention: message on
+ *     stdout + exit(1) (src/allocator.cpp:31-37, include/io/mmf.hpp:188-189).
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with CFS_ERR_NO_DEVICE.
+ *   - indices are 32-bit like the reference's IndexT=int instantiations
+ *     (src/cfs.cpp:11-12); values are float or double (is_double).
+ *   - one process drives one GPU (cfs_cuda_init); multi-GPU runs are one
+ *     process per GPU, each holding a row shard (cfs_cuda_matrix_create_shard).
+ */
+#ifndef CFS_CUDA_H
+#define CFS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFS_OK 0
+#define CFS_ERR_CUDA 1      /* a CUDA runtime call failed                    */
+#define CFS_ERR_INVALID 2   /* bad argument                                  */
+#define CFS_ERR_NO_DEVICE 3 /* no CUDA device / wrong architecture           */
+#define CFS_ERR_STATE 4     /* call order (e.g. spmv before tune)            */
+#define CFS_ERR_TOO_LARGE 5 /* reference-compatible metadata infeasible      */
+
+#define CFS_TUNING_NONE 0       /* util::Tuning::None       platform.hpp:22 */
+#define CFS_TUNING_AGGRESSIVE 1 /* util::Tuning::Aggressive platform.hpp:22 */
+
+typedef struct cfs_matrix_s *cfs_mat_t;
+
+/* ---- runtime: replaces include/utils/runtime.hpp:22 / src/runtime.cpp:10-21
+ * (get_num_threads picks the partition count; here the process also picks
+ * its GPU). */
+int cfs_cuda_device_count(int *count);
+int cfs_cuda_init(int device);
+const char *cfs_cuda_last_error(void);
+const char *cfs_cuda_version(void);
+
+/* ---- allocator: backs internal_alloc / internal_free
+ * (include/utils/allocator.hpp:11-12, src/allocator.cpp:8-43).
+ * 64-byte aligned like the reference; page-locked when a GPU is present so the
+ * host vectors the bench/test allocate are DMA-able. Returns NULL on failure
+ * (the C++ wrapper prints and exit(1)s like the reference). */
+void *cfs_cuda_host_alloc(size_t bytes);
+void cfs_cuda_host_free(void *ptr);
+
+/* ---- matrix construction: replaces CSRMatrix(rowptr, colind, values, nrows,
+ * ncols, symmetric, ...) (include/matrix/csr_matrix.tpp:114-144) and is what
+ * the file constructor (csr_matrix.tpp:9-111) calls after the MMF parse.
+ * FULL (expanded) CSR, 0-based. rowptr/colind/values may be host or device
+ * pointers; host arrays are copied to the GPU, device arrays are borrowed until
+ * cfs_cuda_matrix_tune returns. */
+int cfs_cuda_matrix_create(cfs_mat_t *out, int32_t nrows, int32_t ncols,
+                           const int32_t *rowptr, const int32_t *colind,
+                           const void *values, int is_double, int symmetric);
+
+/* Multi-GPU row shard: this GPU owns global rows [row_begin, row_end) of an
+ * (global_nrows x global_nrows) symmetric matrix (the reference's thread
+ * partition, csr_matrix.tpp:404-435, lifted to GPUs). rowptr is shard-local
+ * (row_end-row_begin+1 entries, starting at 0), colind holds GLOBAL ids. */
+int cfs_cuda_matrix_create_shard(cfs_mat_t *out, int32_t global_nrows,
+                                 int32_t row_begin, int32_t row_end,
+                                 const int32_t *rowptr, const int32_t *colind,
+                                 const void *values, int is_double);
+
+/* ---- preprocessing: replaces CSRMatrix::tune (csr_matrix.tpp:231-310), i.e.
+ * partition_by_nrows (404-435) + compress_symmetry (1684-1716) +
+ * conflict_free_aposteriori (1206-1639) + color_greedy (2010-2213), all on the
+ * GPU. nparts is the reference's P (= CFS_NUM_THREADS): it fixes the
+ * reference-compatible metadata (row_split, per-partition lower CSR, conflict
+ * graph, colours, ranges) that cfs_cuda_matrix_export returns bit-exactly.
+ * The GPU execution layout (sliced, nnz-balanced lower triangle) is built in
+ * the same call. Returns CFS_ERR_TOO_LARGE if the conflict graph of the
+ * reference is infeasible for this input (the SpMV path is still usable). */
+int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning);
+
+void cfs_cuda_matrix_destroy(cfs_mat_t m); /* ~CSRMatrix, csr_matrix.tpp:147 */
+
+typedef struct cfs_matrix_info {
+  int32_t nrows, ncols;     /* of this shard's owned rows / global columns   */
+  int32_t row_begin;        /* first owned global row (0 unless sharded)     */
+  int32_t halo_begin;       /* smallest global column referenced (<= row_begin) */
+  int64_t nnz_full;         /* nnz() of the reference: expanded count        */
+  int64_t nnz_low, nnz_diag;
+  int32_t nparts, ncolors, nranges;
+  int32_t symmetric, is_double, tuned, refmeta; /* refmeta: metadata present  */
+  int64_t size_bytes;       /* size() of the reference, csr_matrix.tpp:191    */
+  int64_t device_bytes;     /* bytes this matrix really holds in HBM          */
+  int64_t algorithmic_bytes;/* bytes one SpMV must move       */
+  int64_t nvrows, nslices, padded_entries; /* execution layout statistics    */
+  int64_t nconflict_edges;
+} cfs_matrix_info;
+
+int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info);
+
+/* ---- SpMV: replaces dense_vector_multiply / spmv_fn
+ * (include/matrix/csr_matrix.hpp:67-70), i.e. cpu_mv_sym_conflict_free_v2
+ * (csr_matrix.tpp:2966-3028), cpu_mv_sym_serial (2707-2729) and, for
+ * symmetric == 0, cpu_mv (2684-2704).
+ * cfs_cuda_spmv is synchronous and accepts host, pinned or device pointers
+ * (y fully overwritten on return, like the reference).
+ * cfs_cuda_spmv_async takes DEVICE vectors and a cudaStream_t; for a shard the
+ * vectors are the extended local vectors covering global rows
+ * [halo_begin, row_end). */
+int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x);
+int cfs_cuda_spmv_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                        void *stream);
+
+/* ---- metadata export (device -> host), for bit-exact parity with the
+ * reference's private members (csr_matrix.hpp:96-124, 221-277).
+ * dst == NULL: only *count is written. Element types: int32 except
+ * LOWER_VALUES / DIAGONAL / SELL_VAL (matrix precision). */
+enum {
+  CFS_META_ROW_SPLIT = 1,  /* row_split_[P+1]                                */
+  CFS_META_PART_NNZ_LOW,   /* SymThreadData::nnz_low_ per partition          */
+  CFS_META_LOWER_ROWPTR,   /* per-partition local rowptr_, concatenated N+P   */
+  CFS_META_LOWER_COLIND,   /* colind_ (global ids), concatenated             */
+  CFS_META_LOWER_VALUES,   /* values_, concatenated                          */
+  CFS_META_DIAGONAL,       /* diagonal_, concatenated (= N)                  */
+  CFS_META_WEIGHT,         /* WeightedVertex::weight per 16-row block        */
+  CFS_META_ADJ_PTR,        /* conflict graph, CSR with ascending neighbours  */
+  CFS_META_ADJ,
+  CFS_META_COLOR_FIRST,    /* colours after first-fit                        */
+  CFS_META_COLOR,          /* colours after balancing (color_map)            */
+  CFS_META_RANGE_PTR,      /* range_ptr_ per partition, P*(ncolors+1)        */
+  CFS_META_PART_NRANGES,   /* SymThreadData::nranges_                        */
+  CFS_META_RANGE_START,    /* range_start_ (local rows), concatenated        */
+  CFS_META_RANGE_END,      /* range_end_ (inclusive), concatenated           */
+  CFS_META_SELL_SLICE_PTR = 100, /* execution layout, for property tests     */
+  CFS_META_SELL_VROW,
+  CFS_META_SELL_COL,
+  CFS_META_SELL_VAL
+};
+int cfs_cuda_matrix_export(cfs_mat_t m, int what, void *dst_host,
+                           size_t capacity_elems, size_t *count);
+
+/* ---- synthetic inputs (bench/test plumbing; cfs_gen.h holds the definition
+ * shared with the oracle). Device-side so that a GPU can build its own shard
+ * of the BASELINE.json configs in place. */
+struct cfs_gen_spec;
+int cfs_gen_host_count(const struct cfs_gen_spec *spec, int64_t row_begin,
+                       int64_t row_end, int32_t *rowptr);
+int cfs_gen_host_fill(const struct cfs_gen_spec *spec, int64_t row_begin,
+                      int64_t row_end, const int32_t *rowptr, int32_t *colind,
+                      void *values, int is_double);
+int cfs_gen_host_x(uint64_t seed, int64_t begin, int64_t end, void *x,
+                   int is_double);
+int cfs_cuda_gen_count(const struct cfs_gen_spec *spec, int64_t row_begin,
+                       int64_t row_end, int32_t *rowptr_dev, int64_t *nnz);
+int cfs_cuda_gen_fill(const struct cfs_gen_spec *spec, int64_t row_begin,
+                      int64_t row_end, const int32_t *rowptr_dev,
+                      int32_t *colind_dev, void *values_dev, int is_double);
+int cfs_cuda_gen_x(uint64_t seed, int64_t begin, int64_t end, void *x_dev,
+                   int is_double);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFS_CUDA_H */
