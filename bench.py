@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- symmetric SpMV throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is ONE SpMV y = A*x over the whole (sharded) matrix with x, y and the
+matrix resident in HBM. N=1 runs BASELINE.json configs[1]: the 27-point
+Laplacian 200^3, double precision. N>1 is the weak-scaling family that ends in
+configs[4] (400^3 on 8 GPUs): every GPU owns 8 M rows, rows are split in
+contiguous blocks (the reference's row partitioning lifted to GPUs), x halos
+and the transposed y contributions that cross a block boundary are exchanged
+every step.
+
+`--impl reference` times the reference's own OpenMP CFS path (the unmodified
+reference compiled into oracle/_ref) on the host cores, rank 0 only.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "symmetric SpMV GFLOP/s (2*nnz_full per SpMV)"
+UNIT = "GFLOP/s"
+XSEED = 1
+# weak-scaling family: 8 M rows per GPU; N=1 is configs[1], N=8 is configs[4]
+GRIDS = {1: (200, 200, 200), 2: (200, 200, 400), 4: (200, 400, 400),
+         8: (400, 400, 400)}
+
+
+def grid_for(n_gpus):
+    if n_gpus in GRIDS:
+        return GRIDS[n_gpus]
+    return (200, 200, 200 * n_gpus)
+
+
+def lap27_nnz_full(nx, ny, nz):
+    return (3 * nx - 2) * (3 * ny - 2) * (3 * nz - 2)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the GPU is under load"""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,"
+              "clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+               "sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.samples = []  # (t, sm, sm_max, power, [reasons])
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.device_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm, smax = float(parts[1]), float(parts[2])
+                power = float(parts[3]) if parts[3][0].isdigit() else 0.0
+            except Exception:
+                continue
+            reasons = [r for r, p in zip(self.REASONS, parts[4:8])
+                       if p.lower().startswith("active")]
+            self.samples.append((time.time(), sm, smax, power, reasons))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1, fallback_window=None):
+        def pick(a, b):
+            return [s for s in self.samples if a <= s[0] <= b]
+        inside = pick(t0, t1)
+        where = "during the timed region"
+        if not inside and fallback_window is not None:
+            inside = pick(*fallback_window)
+            where = ("timed region shorter than the sampling period; sampled "
+                     "during an identical untimed loop right after it")
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+                    "samples": 0, "sampled": "nvidia-smi gave no samples"}
+        sm = sorted(s[1] for s in inside)
+        reasons = sorted(set(r for s in inside for r in s[4]))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": inside[0][2],
+                "power_w_max": max(s[3] for s in inside),
+                "reasons": reasons, "samples": len(inside), "sampled": where}
+
+
+def run_reference(args, rank, world):
+    """the reference's own CPU implementation of the path, host cores"""
+    if rank != 0:
+        return
+    from oracle import oracle
+    nx, ny, nz = grid_for(args.gpus)
+    sample_grid = (200, 200, 200)  # one GPU's share of the workload
+    cores = os.cpu_count() or 1
+    P = min(cores, 96)  # MaxThreads of the reference (runtime.hpp:15)
+    n = sample_grid[0] * sample_grid[1] * sample_grid[2]
+    while P > 1 and not oracle.valid_partition_count(n, P):
+        P -= 1
+    loops = max(2, min(args.steps, 400))
+    spec = "gen:lap27:%d:%d:%d" % sample_grid
+    if not oracle.ref_available():
+        # the compiled reference always travels with the repo; if it is gone,
+        # time the C restatement (single thread) instead
+        out = time_oracle_port(sample_grid, loops)
+    else:
+        r = oracle.run_ref_bench(spec, P, "d", XSEED, loops, timeout=3000)
+        out = {"value": r["gflops"], "ms": r["t_spmv_s"] * 1e3, "cores": P,
+               "kind": "reference", "preproc_s": r["preproc_s"],
+               "ncolors": r["ncolors"]}
+    sample = ("27-pt Laplacian %dx%dx%d double (%s), %d timed SpMVs after %d "
+              "warm-up, CFS_NUM_THREADS=%d of %d host cores" % (
+                  sample_grid + ("the full N=1 workload" if args.gpus == 1 else
+                                 "one GPU's share of the N=%d workload" % args.gpus,
+                                 loops, loops // 2, out["cores"], cores)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": out["value"],
+        "unit": UNIT, "n_gpus": args.gpus, "steps": loops,
+        "warmup": loops // 2, "ms_per_step": out["ms"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": out["value"], "unit": UNIT,
+                         "cores": out["cores"], "kind": out["kind"],
+                         "sample": sample},
+        "e2e": {"value": out["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_oracle_port(grid, loops):
+    import numpy as np
+    from cfs_spmv_b200 import capi, gen
+    from oracle import oracle
+    spec = capi.GenSpec.laplacian(27, *grid)
+    rp, ci, v = capi.gen_host_csr(spec)
+    o = oracle.Oracle(rp, ci, v, 1)
+    x = gen.gen_x(XSEED, len(rp) - 1)
+    o.spmv(x)
+    t0 = time.perf_counter()
+    for _ in range(loops):
+        o.spmv(x)
+    dt = (time.perf_counter() - t0) / loops
+    return {"value": 2.0 * int(rp[-1]) * 1e-9 / dt, "ms": dt * 1e3, "cores": 1,
+            "kind": "port"}
+
+
+def workload_config(n_gpus):
+    nx, ny, nz = grid_for(n_gpus)
+    return {
+        "workload": "27-point Laplacian %dx%dx%d, double, lower triangle "
+                    "stored (BASELINE.json configs[%d]%s)" % (
+                        nx, ny, nz, 1 if n_gpus == 1 else 4,
+                        "" if n_gpus in (1, 8) else " weak-scaling family"),
+        "rows": nx * ny * nz, "nnz_full": lap27_nnz_full(nx, ny, nz),
+        "rows_per_gpu": nx * ny * nz // n_gpus,
+        "partition": "contiguous row blocks, one per GPU",
+        "cache": "inputs larger than L2 (1.46 GB streamed per GPU per step vs "
+                 "126 MB L2); no flush needed",
+    }
+
+
+def cpu_baseline(args):
+    """bounded CPU sample next to the GPU number (rank 0, N=1 only)"""
+    from oracle import oracle
+    grid = (200, 200, 200)
+    cores = os.cpu_count() or 1
+    P = min(cores, 96)
+    n = grid[0] * grid[1] * grid[2]
+    while P > 1 and not oracle.valid_partition_count(n, P):
+        P -= 1
+    loops = 10
+    try:
+        if oracle.ref_available():
+            r = oracle.run_ref_bench("gen:lap27:%d:%d:%d" % grid, P, "d", XSEED,
+                                     loops, timeout=1500)
+            return {"value": r["gflops"], "unit": UNIT, "cores": P,
+                    "kind": "reference",
+                    "sample": "full N=1 workload (27-pt 200^3 double), %d timed "
+                              "SpMVs after %d warm-up, OpenMP CFS with "
+                              "CFS_NUM_THREADS=%d of %d host cores, preproc "
+                              "%.1f s, %d colours" % (loops, loops // 2, P, cores,
+                                                      r["preproc_s"], r["ncolors"])}
+        out = time_oracle_port((100, 100, 100), 5)
+        return {"value": out["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "oracle C restatement, 27-pt 100^3 double, 5 SpMVs, "
+                          "1 thread (oracle/_ref missing)"}
+    except Exception as e:  # a baseline failure must not void the GPU number
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                "sample": "failed: %r" % (e,)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cfs_spmv_b200 import capi
+    from cfs_spmv_b200.dist import ShardedSpMV
+
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torchrun "
+                         "--nproc-per-node %d" % (args.gpus, world, args.gpus))
+    torch.cuda.set_device(local_rank)
+    capi.init(local_rank)  # fails loudly without a B200 / the native library
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, ny, nz = grid_for(world)
+    spec = capi.GenSpec.laplacian(27, nx, ny, nz)
+    nnz_full = lap27_nnz_full(nx, ny, nz)
+    t_setup = time.time()
+    op = ShardedSpMV(spec, rank, world, is_double=True, xseed=XSEED)
+    info = op.info
+    setup_s = time.time() - t_setup
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(args.warmup):
+        op.step()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        op.step()
+    e1.record(stream)
+    barrier()
+    w1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = ms.item()
+
+    # identical untimed loop (>= 1 s) so that nvidia-smi (50 ms period) is
+    # guaranteed samples under this load even for a short timed region
+    fb0 = time.time()
+    reps = 0
+    while time.time() - fb0 < 1.0 and (w1 - w0) < 0.5:
+        for _ in range(50):
+            op.step()
+        torch.cuda.synchronize()
+        reps += 1
+    fb1 = time.time()
+
+    # dominant kernel alone: CUDA events directly around every launch
+    k_iters = max(10, min(args.steps, 200))
+    barrier()
+    _, kern_ms = op.matrix.spmv_timed(op.y_ext, op.x_ext, k_iters,
+                                      stream.cuda_stream)
+    kernel_ms_avg = kern_ms / k_iters
+    barrier()
+
+    # end to end through the host-pointer entry point
+    e2e_steps = max(5, min(args.steps, 30))
+    e2e_ms, h2d, d2h = op.e2e(e2e_steps)
+    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    barrier()
+    if sampler:
+        sampler.stop()
+
+    checksum = op.checksum()
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = info["algorithmic_bytes"]
+        achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        ms_per_step = total_ms / args.steps
+        line = {
+            "metric": METRIC,
+            "value": 2.0 * nnz_full * 1e-9 / (ms_per_step * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(world), setup_s=round(setup_s, 2),
+                           exchange=op.exchange_desc,
+                           layout={k: info[k] for k in
+                                   ("nnz_low", "nvrows", "nslices",
+                                    "padded_entries", "device_bytes")}),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src,
+                "frac_of_8000": achieved / 8000.0,
+                "kernel": "sym_spmv_sell_kernel<double>",
+                "kernel_ms": kernel_ms_avg,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "hbm_gbs_whole_step": alg_bytes / (ms_per_step * 1e-3) / 1e9,
+            },
+            "e2e": {
+                "value": 2.0 * nnz_full * 1e-9 / (e2e_t.item() / e2e_steps * 1e-3),
+                "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                "path": "cfs_cuda_spmv(host y, host x): pinned H2D + kernel + D2H"
+                        if world == 1 else
+                        "pinned H2D of x shard+halo, kernel, NCCL y halo, D2H",
+            },
+            "gpu_launches": args.steps * world,
+            "clocks": sampler.summary(w0, w1, (fb0, fb1)),
+            "checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

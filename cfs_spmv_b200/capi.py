@@ -31,7 +31,8 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_version", "cfs_cuda_host_alloc", "cfs_cuda_host_free",
     "cfs_cuda_matrix_create", "cfs_cuda_matrix_create_shard",
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
-    "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_matrix_export",
+    "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_timed",
+    "cfs_cuda_matrix_export",
     "cfs_gen_host_count", "cfs_gen_host_fill", "cfs_gen_host_x",
     "cfs_cuda_gen_count", "cfs_cuda_gen_fill", "cfs_cuda_gen_x",
 )
@@ -119,6 +120,9 @@ def lib():
     L.cfs_cuda_matrix_info.argtypes = [vp, ctypes.POINTER(MatrixInfo)]
     L.cfs_cuda_spmv.argtypes = [vp, vp, vp]
     L.cfs_cuda_spmv_async.argtypes = [vp, vp, vp, vp]
+    L.cfs_cuda_spmv_timed.argtypes = [vp, vp, vp, vp, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_float),
+                                      ctypes.POINTER(ctypes.c_float)]
     L.cfs_cuda_matrix_export.argtypes = [vp, ctypes.c_int, vp, sz,
                                          ctypes.POINTER(sz)]
     gs = ctypes.POINTER(GenSpec)
@@ -209,6 +213,14 @@ class Matrix:
     def spmv_async(self, y_dev, x_dev, stream=0):
         check(lib().cfs_cuda_spmv_async(self._h, _ptr(y_dev), _ptr(x_dev),
                                         stream))
+
+    def spmv_timed(self, y_dev, x_dev, iters, stream=0):
+        """-> (total_ms, kernel_ms) summed over `iters` SpMVs"""
+        total, kern = ctypes.c_float(0), ctypes.c_float(0)
+        check(lib().cfs_cuda_spmv_timed(self._h, _ptr(y_dev), _ptr(x_dev),
+                                        stream, iters, ctypes.byref(total),
+                                        ctypes.byref(kern)))
+        return total.value, kern.value
 
     def export(self, name):
         sel = META[name]

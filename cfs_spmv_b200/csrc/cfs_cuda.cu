@@ -460,6 +460,44 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   return CFS_OK;
 }
 
+int cfs_cuda_spmv_timed(cfs_mat_t m, void *y_dev, const void *x_dev,
+                        void *stream, int iters, float *total_ms,
+                        float *kernel_ms) {
+  if (!m || !y_dev || !x_dev || iters < 1 || iters > 65536)
+    return CFS_ERR_INVALID;
+  if (!m->tuned || !m->symmetric) {
+    set_error("cfs_cuda_spmv_timed: needs a tuned symmetric matrix");
+    return CFS_ERR_STATE;
+  }
+  CFS_CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev((size_t)2 * iters + 2);
+  for (auto &e : ev)
+    CFS_CUDA_TRY(cudaEventCreate(&e));
+  int status = CFS_OK;
+  cudaEventRecord(ev[2 * iters], s);
+  for (int i = 0; i < iters && status == CFS_OK; ++i)
+    status = launch_sym_spmv(m, y_dev, x_dev, s, ev[2 * i], ev[2 * i + 1]);
+  cudaEventRecord(ev[2 * iters + 1], s);
+  if (status == CFS_OK && cudaStreamSynchronize(s) != cudaSuccess)
+    status = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+  if (status == CFS_OK) {
+    float sum = 0, t = 0;
+    for (int i = 0; i < iters; ++i) {
+      cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+      sum += t;
+    }
+    if (kernel_ms)
+      *kernel_ms = sum;
+    cudaEventElapsedTime(&t, ev[2 * iters], ev[2 * iters + 1]);
+    if (total_ms)
+      *total_ms = t;
+  }
+  for (auto &e : ev)
+    cudaEventDestroy(e);
+  return status;
+}
+
 // ---- metadata export ------------------------------------------------------
 static int copy_out(const void *dev, size_t n, size_t elem, void *dst,
                     size_t cap, size_t *count) {

@@ -114,8 +114,10 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s);
 // reference metadata (refmeta.cu)
 int build_refmeta(cfs_matrix_s *m, cudaStream_t s);
 // kernels (spmv.cu)
+// ev0/ev1 (optional) are recorded directly before/after the kernel launch
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
-                    cudaStream_t s);
+                    cudaStream_t s, cudaEvent_t ev0 = nullptr,
+                    cudaEvent_t ev1 = nullptr);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,
                     cudaStream_t s);
 

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kSpmvThreads)
 } // namespace
 
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
-                    cudaStream_t s) {
+                    cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
   const size_t vs = m->vsize();
   const size_t ext_len = (size_t)(m->row_begin + m->nrows - m->halo_begin);
   CFS_CUDA_TRY(cudaMemsetAsync(y_ext, 0, ext_len * vs, s));
@@ -155,6 +155,8 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
     return CFS_OK;
   const unsigned grid = (unsigned)((m->nslices * 32 + kSpmvThreads - 1) /
                                    kSpmvThreads);
+  if (ev0)
+    CFS_CUDA_TRY(cudaEventRecord(ev0, s));
   if (m->is_double) {
     const double *xb = (const double *)x_ext - m->halo_begin;
     double *yb = (double *)y_ext - m->halo_begin;
@@ -169,6 +171,8 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
         (const float *)m->sell_val.p, (const float *)m->diagonal.p, xb, yb);
   }
   CFS_CUDA_TRY(cudaGetLastError());
+  if (ev1)
+    CFS_CUDA_TRY(cudaEventRecord(ev1, s));
   return CFS_OK;
 }
 

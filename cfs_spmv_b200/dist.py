@@ -1,0 +1,209 @@
+"""Multi-GPU runtime: the reference's 1-D contiguous row partitioning
+(partition_by_nrows / partition_by_nnz, include/matrix/csr_matrix.tpp:404-541)
+lifted from OpenMP threads to GPUs, one process per GPU.
+
+GPU g owns global rows [R_g, R_{g+1}). It stores the lower-triangle entries of
+its rows; their columns reach down to halo_begin_g <= R_g, so
+
+  * it needs x[halo_begin_g : R_g) from the owners below it   (x halo), and
+  * it produces transposed contributions to y[halo_begin_g : R_g), the
+    reference's "direct conflicts" (csr_matrix.tpp:1447), which the owners must
+    add to their y                                               (y halo).
+
+Both are point-to-point exchanges with the few ranks directly below (one for
+stencil / banded matrices), done over NCCL (NVLink) with torch.distributed as
+plumbing. No dense reduce-scatter of y: only the touched strip moves.
+"""
+import numpy as np
+
+
+def row_blocks(nrows, world, align=16):
+    """contiguous, `align`-row aligned (the reference's BlkFactor) equal-row
+    blocks: bounds[g] .. bounds[g+1]"""
+    bounds = [min(nrows, (nrows * g // world) // align * align)
+              for g in range(world)] + [nrows]
+    return bounds
+
+
+def nnz_balanced_blocks(row_nnz_prefix, world, align=16):
+    """contiguous blocks with ~equal nnz (partition_by_nnz semantics,
+    csr_matrix.tpp:438-541): row_nnz_prefix[i] = nnz of rows < i"""
+    nrows = len(row_nnz_prefix) - 1
+    total = int(row_nnz_prefix[-1])
+    bounds = [0]
+    for g in range(1, world):
+        target = total * g // world
+        r = int(np.searchsorted(row_nnz_prefix, target, side="left"))
+        r = min(nrows, (r + align // 2) // align * align)
+        bounds.append(max(r, bounds[-1]))
+    bounds.append(nrows)
+    return bounds
+
+
+def plan_exchange(ranges, rank):
+    """ranges[g] = (halo_begin, row_begin, row_end) of every rank.
+    Returns (recv_x, send_x): lists of (peer, global_lo, global_hi).
+      recv_x: x rows this rank must receive from `peer` (its halo, cut by owner)
+      send_x: x rows this rank owns that `peer` needs
+    The y halo travels the same segments in the opposite direction."""
+    h, b, e = ranges[rank]
+    recv_x, send_x = [], []
+    for peer, (ph, pb, pe) in enumerate(ranges):
+        if peer == rank:
+            continue
+        lo, hi = max(h, pb), min(b, pe)  # my halo inside peer's rows
+        if lo < hi:
+            recv_x.append((peer, lo, hi))
+        lo, hi = max(ph, b), min(pb, e)  # peer's halo inside my rows
+        if lo < hi:
+            send_x.append((peer, lo, hi))
+    return recv_x, send_x
+
+
+class HaloExchanger:
+    """x-halo gather and y-halo scatter-add between row-block owners.
+    Works on any torch.distributed backend (NCCL on GPUs, gloo in the CPU
+    tests); vectors are the extended local vectors covering [halo_begin,
+    row_end)."""
+
+    def __init__(self, ranges, rank, like):
+        import torch
+        self.rank = rank
+        self.h, self.b, self.e = ranges[rank]
+        self.recv_x, self.send_x = plan_exchange(ranges, rank)
+        self.world = len(ranges)
+        # staging for incoming y contributions
+        self.y_in = [torch.empty(hi - lo, dtype=like.dtype, device=like.device)
+                     for (_, lo, hi) in self.send_x]
+        self.bytes_per_step = sum((hi - lo) for _, lo, hi in
+                                  self.recv_x + self.send_x) * like.element_size()
+
+    def _sl(self, lo, hi):
+        return slice(lo - self.h, hi - self.h)
+
+    def exchange_x(self, x_ext):
+        import torch.distributed as dist
+        if self.world == 1 or not (self.recv_x or self.send_x):
+            return
+        ops = [dist.P2POp(dist.isend, x_ext[self._sl(lo, hi)], peer)
+               for peer, lo, hi in self.send_x]
+        ops += [dist.P2POp(dist.irecv, x_ext[self._sl(lo, hi)], peer)
+                for peer, lo, hi in self.recv_x]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def reduce_y(self, y_ext):
+        import torch.distributed as dist
+        if self.world == 1 or not (self.recv_x or self.send_x):
+            return
+        ops = [dist.P2POp(dist.isend, y_ext[self._sl(lo, hi)], peer)
+               for peer, lo, hi in self.recv_x]
+        ops += [dist.P2POp(dist.irecv, buf, peer)
+                for buf, (peer, lo, hi) in zip(self.y_in, self.send_x)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for buf, (peer, lo, hi) in zip(self.y_in, self.send_x):
+            y_ext[self._sl(lo, hi)] += buf
+
+
+class ShardedSpMV:
+    """One rank's share of y = A*x for a generated matrix (bench / tests)."""
+
+    def __init__(self, spec, rank, world, is_double=True, xseed=1):
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.rank, self.world = rank, world
+        n = spec.nrows
+        bounds = row_blocks(n, world)
+        b, e = bounds[rank], bounds[rank + 1]
+        rp, ci, v = capi.gen_device_csr(spec, b, e, is_double)
+        if world == 1:
+            self.matrix = capi.Matrix(n, n, rp, ci, v, is_double, True)
+        else:
+            self.matrix = capi.Matrix(0, 0, rp, ci, v, is_double, True,
+                                      shard=(n, b, e))
+        self.matrix.tune(1)
+        del rp, ci, v
+        torch.cuda.empty_cache()
+        self.info = self.matrix.info()
+        h = self.info["halo_begin"]
+        self.h, self.b, self.e = h, b, e
+        if world > 1:
+            mine = torch.tensor([h, b, e], dtype=torch.int64, device="cuda")
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            ranges = [tuple(int(v) for v in t.tolist()) for t in allr]
+        else:
+            ranges = [(h, b, e)]
+        self.x_ext = capi.gen_device_x(xseed, h, e, is_double)
+        # the halo part of x is (re)filled by exchange_x every step
+        self.y_ext = torch.zeros_like(self.x_ext)
+        self.halo = HaloExchanger(ranges, rank, self.x_ext)
+        nh = len(self.halo.recv_x) + len(self.halo.send_x)
+        self.exchange_desc = (
+            "none (single GPU)" if world == 1 else
+            "NCCL P2P per step: x halo down-up, y halo strip add; "
+            "%d neighbour segments, %d bytes on rank %d" % (
+                nh, self.halo.bytes_per_step, rank))
+        self._host = None
+
+    def step(self):
+        import torch
+        s = torch.cuda.current_stream().cuda_stream
+        self.halo.exchange_x(self.x_ext)
+        self.matrix.spmv_async(self.y_ext, self.x_ext, s)
+        self.halo.reduce_y(self.y_ext)
+
+    def y_owned(self):
+        return self.y_ext[self.b - self.h:]
+
+    def checksum(self):
+        import torch
+        import torch.distributed as dist
+        t = self.y_owned().sum().reshape(1)
+        if self.world > 1:
+            dist.all_reduce(t)
+        return float(t.item())
+
+    def e2e(self, steps):
+        """the same SpMV with HOST vectors: pinned H2D of x, kernel (+ y halo
+        exchange), D2H of y, every step. Returns (total_ms, h2d, d2h bytes)."""
+        import time
+        import torch
+        n_own = self.e - self.b
+        if self.world == 1:
+            x_host = self.x_ext.cpu().pin_memory()
+            y_host = torch.empty_like(x_host).pin_memory()
+            self.matrix.spmv(y_host, x_host)  # allocates the staging buffers
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.matrix.spmv(y_host, x_host)  # synchronous C ABI call
+            ms = (time.perf_counter() - t0) * 1e3
+            err = (y_host - self.y_owned().cpu()).abs().max().item()
+            scale = self.y_owned().abs().max().item()
+            assert err <= 1e-9 * max(scale, 1.0), "e2e result differs"
+            return ms, x_host.numel() * x_host.element_size(), \
+                y_host.numel() * y_host.element_size()
+        x_host = self.x_ext.cpu().pin_memory()       # owned rows + halo
+        y_host = torch.empty(n_own, dtype=self.x_ext.dtype).pin_memory()
+        s = torch.cuda.current_stream()
+
+        def one():
+            self.x_ext.copy_(x_host, non_blocking=True)
+            self.matrix.spmv_async(self.y_ext, self.x_ext, s.cuda_stream)
+            self.halo.reduce_y(self.y_ext)
+            y_host.copy_(self.y_owned(), non_blocking=True)
+            s.synchronize()
+
+        one()
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        ms = (time.perf_counter() - t0) * 1e3
+        return ms, x_host.numel() * x_host.element_size(), \
+            y_host.numel() * y_host.element_size()

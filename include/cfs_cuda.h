@@ -122,6 +122,15 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x);
 int cfs_cuda_spmv_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                         void *stream);
 
+/* Measurement aid for bench.py (bench_spmv_mmf.cpp:162-167 times the same
+ * loop with omp_get_wtime): runs `iters` SpMVs on `stream` and returns the
+ * summed device time of the SpMV KERNEL alone (kernel_ms, CUDA events placed
+ * directly around each kernel launch) and of the whole loop including the y
+ * initialisation (total_ms). Synchronises the stream. */
+int cfs_cuda_spmv_timed(cfs_mat_t m, void *y_dev, const void *x_dev,
+                        void *stream, int iters, float *total_ms,
+                        float *kernel_ms);
+
 /* ---- metadata export (device -> host), for bit-exact parity with the
  * reference's private members (csr_matrix.hpp:96-124, 221-277).
  * dst == NULL: only *count is written. Element types: int32 except

@@ -1,0 +1,303 @@
+"""Parity of the CUDA path (through the C ABI) with the reference.
+
+  * preprocessing metadata: BIT-EXACT against the golden dumps of the compiled
+    reference (tests/golden) and against the CPU oracle on fresh inputs;
+  * y: normwise relative error <= 1e-12 (double) / 1e-5 (single) against the
+    reference's CFS kernel output (BASELINE.json north_star) -- the reduction
+    order differs, so not bitwise.
+"""
+import numpy as np
+import pytest
+
+import cases
+from cfs_spmv_b200 import capi, gen
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+GRAPH_KEYS = ("weight", "adj_ptr", "adj", "color_first", "color")
+
+
+def _check_metadata(md, ref, who):
+    for k in oracle.SCALAR_KEYS:
+        assert int(md[k]) == int(ref[k]), (who, k, int(md[k]), int(ref[k]))
+    for k in oracle.METADATA_KEYS:
+        r = ref[k] if not hasattr(ref, "files") else cases.gold_array(ref, k)
+        assert np.array_equal(md[k], r), (who, k)
+        assert md[k].size == 0 or md[k].dtype == r.dtype, (who, k)
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=cases.case_id)
+def test_golden_parity(gpu, case):
+    name, P, prec = case
+    gold = np.load(cases.golden_path(case))
+    rp, ci, v, x = cases.case_inputs(case)
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(P)
+    _check_metadata(A.metadata(), gold, "golden")
+    # conflict graph and colours against the (pinned) oracle
+    o = oracle.Oracle(rp, ci, v, P)
+    if P > 1:
+        for k in GRAPH_KEYS:
+            assert np.array_equal(A.export(k), getattr(o, k)), k
+    # y, twice on the same buffer (test_spmv_mmf.cpp:80-83), dirty start
+    y = np.full(len(x), 123.0, dtype=x.dtype)
+    for _ in range(2):
+        A.spmv(y, x)
+        assert cases.normwise_rel_err(y, gold["y"]) <= cases.TOL[prec]
+    # the reference's own acceptance test against plain CSR (isEqual)
+    eps = 1e-8 if prec == "d" else 1e-4
+    assert np.all(np.abs(y - gold["y_csr"]) <= eps * np.abs(y) + 1e-300)
+    A.close()
+
+
+@pytest.mark.parametrize("case", [c for c in cases.CASES if c[1] in (1, 4)],
+                         ids=cases.case_id)
+def test_csr_comparator_kernel(gpu, case):
+    """Format::csr path (cpu_mv), the comparator of test_spmv_mmf.cpp:85-89"""
+    name, P, prec = case
+    gold = np.load(cases.golden_path(case))
+    rp, ci, v, x = cases.case_inputs(case)
+    A = capi.Matrix.from_csr(rp, ci, v, symmetric=False)
+    A.tune(P, tuning=0)
+    y = np.zeros(len(x), dtype=x.dtype)
+    A.spmv(y, x)
+    assert cases.normwise_rel_err(y, gold["y_csr"]) <= cases.TOL[prec]
+    inf = A.info()
+    assert inf["nnz_full"] == int(gold["nnz_full"])
+    A.close()
+
+
+def _decode_layout(A):
+    """execution layout -> list of (row, col, val), for the property test"""
+    sp_ = A.export("sell_slice_ptr")
+    vrow = A.export("sell_vrow")
+    col = A.export("sell_col")
+    val = A.export("sell_val")
+    rows, cols, vals = [], [], []
+    first_seen = {}
+    for s in range(len(sp_) - 1):
+        w = sp_[s + 1] - sp_[s]
+        blk_c = col[sp_[s] * 32:(sp_[s] + w) * 32].reshape(w, 32)
+        blk_v = val[sp_[s] * 32:(sp_[s] + w) * 32].reshape(w, 32)
+        for lane in range(32):
+            tag = vrow[s * 32 + lane]
+            if tag < 0:
+                assert np.all(blk_c[:, lane] == -1)
+                continue
+            r = tag & ((1 << 30) - 1)
+            cont = bool(tag & (1 << 30))
+            assert cont == (r in first_seen), "exactly one first chunk per row"
+            first_seen[r] = True
+            m = blk_c[:, lane] >= 0
+            # real entries first, padding after, never interleaved
+            k = int(m.sum())
+            assert np.all(m[:k]) and not np.any(m[k:])
+            assert k <= 64
+            rows += [r] * k
+            cols += list(blk_c[:k, lane])
+            vals += list(blk_v[:k, lane])
+    return np.array(rows), np.array(cols), np.array(vals), first_seen
+
+
+@pytest.mark.parametrize("name", ["lap27_10", "rmat_9", "ragged_333",
+                                  "diag_only_48", "banded_3000"])
+def test_layout_holds_exactly_the_lower_triangle(gpu, name):
+    rp, ci, v = cases.matrix(name)
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(1)
+    rows, cols, vals, seen = _decode_layout(A)
+    n = len(rp) - 1
+    assert sorted(seen) == list(range(n)), "every row owns a first chunk"
+    o = oracle.Oracle(rp, ci, v, 1)
+    lrp = o.lower_rowptr
+    exp_rows = np.repeat(np.arange(n), np.diff(lrp))
+    # same multiset, and same order inside every row (chunks are in order)
+    assert len(rows) == o.nnz_low
+    order = np.argsort(rows, kind="stable")
+    assert np.array_equal(rows[order], exp_rows)
+    assert np.array_equal(cols[order], o.lower_colind)
+    assert np.array_equal(vals[order], o.lower_values)
+    inf = A.info()
+    assert inf["padded_entries"] >= inf["nnz_low"]
+    A.close()
+
+
+def test_long_rows_are_split(gpu):
+    """an arrow matrix: last row is dense (n-1 lower entries) -> many chunks"""
+    n = 1000
+    rows = np.concatenate([np.arange(n), np.full(n - 1, n - 1), np.arange(n - 1)])
+    cols = np.concatenate([np.arange(n), np.arange(n - 1), np.full(n - 1, n - 1)])
+    vals = np.concatenate([np.full(n, 8.0), np.linspace(-1, 1, n - 1),
+                           np.linspace(-1, 1, n - 1)])
+    order = np.lexsort((cols, rows))
+    rp = np.zeros(n + 1, np.int64)
+    np.add.at(rp, rows + 1, 1)
+    rp = np.cumsum(rp).astype(np.int32)
+    ci, v = cols[order].astype(np.int32), vals[order]
+    x = gen.gen_x(5, n)
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        A = capi.Matrix.from_csr(rp, ci, v.astype(dt))
+        A.tune(1)
+        assert A.info()["nvrows"] == (n - 1) + 16  # ceil(999/64) chunks
+        y = np.zeros(n, dt)
+        A.spmv(y, x.astype(dt))
+        o = oracle.Oracle(rp, ci, v.astype(dt), 1)
+        assert cases.normwise_rel_err(y, o.spmv(x.astype(dt))) <= tol
+        A.close()
+
+
+@pytest.mark.parametrize("points,n,P", [(7, 40, 8), (27, 32, 37), (27, 48, 148)])
+def test_fresh_laplacians_against_oracle(gpu, points, n, P):
+    """non-golden sizes, partition counts up to one per SM (148)"""
+    spec = capi.GenSpec.laplacian(points, n, n, n)
+    rp, ci, v = capi.gen_host_csr(spec)
+    if not oracle.valid_partition_count(len(rp) - 1, P):
+        pytest.skip("P not valid for the reference")
+    x = gen.gen_x(11, len(rp) - 1)
+    o = oracle.Oracle(rp, ci, v, P)
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(P)
+    _check_metadata(A.metadata(), o.metadata(), "oracle")
+    for k in GRAPH_KEYS:
+        assert np.array_equal(A.export(k), getattr(o, k)), k
+    y = np.zeros(len(x))
+    A.spmv(y, x)
+    assert cases.normwise_rel_err(y, o.spmv(x)) <= 1e-12
+    A.close()
+
+
+def test_device_generated_matrix_equals_host_generated(gpu):
+    import torch
+    for spec in (capi.GenSpec.laplacian(27, 9, 8, 7),
+                 capi.GenSpec.laplacian(7, 6, 5, 11),
+                 capi.GenSpec.banded(4000, 300, 152, 9)):
+        rp, ci, v = capi.gen_host_csr(spec)
+        drp, dci, dv = capi.gen_device_csr(spec)
+        assert np.array_equal(drp.cpu().numpy(), rp)
+        assert np.array_equal(dci.cpu().numpy(), ci)
+        assert np.array_equal(dv.cpu().numpy(), v)
+        # shard
+        drp, dci, dv = capi.gen_device_csr(spec, 100, 300, is_double=False)
+        assert np.array_equal(dci.cpu().numpy(), ci[rp[100]:rp[300]])
+        assert np.array_equal(dv.cpu().numpy(),
+                              v[rp[100]:rp[300]].astype(np.float32))
+    x = capi.gen_device_x(3, 10, 1000)
+    assert np.array_equal(x.cpu().numpy(), gen.gen_x(3, 990, begin=10))
+    torch.cuda.synchronize()
+
+
+def test_device_pointers_and_streams(gpu):
+    """device-resident CSR in, device vectors, caller's stream (bench path)"""
+    import torch
+    spec = capi.GenSpec.laplacian(27, 24, 24, 24)
+    n = spec.nrows
+    drp, dci, dv = capi.gen_device_csr(spec)
+    A = capi.Matrix(n, n, drp, dci, dv, True, True)
+    A.tune(1)
+    del drp, dci, dv  # borrowed only until tune() returns
+    torch.cuda.empty_cache()
+    x = capi.gen_device_x(4, 0, n)
+    y = torch.full((n,), 7.0, dtype=torch.float64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            A.spmv_async(y, x, s.cuda_stream)
+    s.synchronize()
+    rp, ci, v = capi.gen_host_csr(spec)
+    o = oracle.Oracle(rp, ci, v, 1)
+    assert cases.normwise_rel_err(y.cpu().numpy(),
+                                  o.spmv(x.cpu().numpy())) <= 1e-12
+    A.close()
+
+
+def test_row_shards_reproduce_the_whole(gpu):
+    """multi-GPU layout on one GPU: G row shards, extended local vectors;
+    summing the halo contributions reproduces the unsharded y"""
+    import torch
+    spec = capi.GenSpec.laplacian(27, 12, 12, 20)
+    n = spec.nrows
+    rp, ci, v = capi.gen_host_csr(spec)
+    x = gen.gen_x(8, n)
+    o = oracle.Oracle(rp, ci, v, 1)
+    y_ref = o.spmv(x)
+    for G in (2, 3, 5):
+        bounds = [(n * g // G) // 16 * 16 for g in range(G)] + [n]
+        y = np.zeros(n)
+        for g in range(G):
+            b, e = bounds[g], bounds[g + 1]
+            srp = (rp[b:e + 1] - rp[b]).astype(np.int32)
+            A = capi.Matrix(0, 0, srp, ci[rp[b]:rp[e]].copy(),
+                            v[rp[b]:rp[e]].copy(), True, True,
+                            shard=(n, b, e))
+            A.tune(1)
+            inf = A.info()
+            h = inf["halo_begin"]
+            assert inf["row_begin"] == b and h <= b
+            assert h == (ci[rp[b]:rp[e]].min() if e > b else b)
+            x_ext = torch.from_numpy(x[h:e].copy()).cuda()
+            y_ext = torch.empty(e - h, dtype=torch.float64, device="cuda")
+            A.spmv_async(y_ext, x_ext, 0)
+            torch.cuda.synchronize()
+            y[h:e] += y_ext.cpu().numpy()
+            A.close()
+        assert cases.normwise_rel_err(y, y_ref) <= 1e-12
+
+
+def test_call_order_and_argument_errors(gpu):
+    rp, ci, v = cases.matrix("lap7_12")
+    A = capi.Matrix.from_csr(rp, ci, v)
+    y = np.zeros(len(rp) - 1)
+    with pytest.raises(capi.CfsError) as e:
+        A.spmv(y, y)
+    assert e.value.code == capi.CFS_ERR_STATE
+    with pytest.raises(capi.CfsError) as e:
+        A.tune(512)  # the reference overshoots row_split_ here
+    assert e.value.code == capi.CFS_ERR_INVALID
+    A.close()
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(2)
+    with pytest.raises(capi.CfsError) as e:
+        A.tune(2)
+    assert e.value.code == capi.CFS_ERR_STATE
+    A.close()
+
+
+def test_full_size_config2_properties(gpu):
+    """BASELINE config 2 (27-pt 200^3, double) at FULL size, through
+    size-independent properties: A*1 is known in closed form, the operator is
+    linear, and x2'(A x1) == x1'(A x2)."""
+    import torch
+    nx = 200
+    spec = capi.GenSpec.laplacian(27, nx, nx, nx)
+    n = spec.nrows
+    drp, dci, dv = capi.gen_device_csr(spec)
+    A = capi.Matrix(n, n, drp, dci, dv, True, True)
+    A.tune(1)
+    del drp, dci, dv
+    torch.cuda.empty_cache()
+    inf = A.info()
+    assert inf["nnz_full"] == (3 * nx - 2) ** 3 == 213847192
+    assert inf["nnz_low"] == 102923596 and inf["nnz_diag"] == n
+    assert inf["algorithmic_bytes"] == 1459083156
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(ones)
+    A.spmv_async(y, ones, 0)
+    # A*1 = 26 - (#neighbours) = 27 - (count per axis product)
+    ax = torch.full((nx,), 3.0, dtype=torch.float64, device="cuda")
+    ax[0] = ax[-1] = 2.0
+    cnt = ax.view(nx, 1, 1) * ax.view(1, nx, 1) * ax.view(1, 1, nx)
+    expect = (27.0 - cnt).reshape(-1)
+    assert torch.equal(y, expect)  # small integers: exact in any order
+    x1 = capi.gen_device_x(1, 0, n)
+    x2 = capi.gen_device_x(2, 0, n)
+    y1, y2, y12 = (torch.empty_like(x1) for _ in range(3))
+    A.spmv_async(y1, x1, 0)
+    A.spmv_async(y2, x2, 0)
+    A.spmv_async(y12, 2.0 * x1 - 3.0 * x2, 0)
+    torch.cuda.synchronize()
+    lin = torch.linalg.norm(y12 - (2.0 * y1 - 3.0 * y2)) / torch.linalg.norm(y12)
+    assert lin.item() <= 1e-12
+    a, b = torch.dot(x2, y1).item(), torch.dot(x1, y2).item()
+    assert abs(a - b) <= 1e-12 * abs(a)
+    A.close()
