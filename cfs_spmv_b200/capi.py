@@ -28,7 +28,7 @@ _VALUE_META = ("lower_values", "diagonal", "sell_val")
 # every symbol include/cfs_cuda.h declares (tests check the library exports all)
 DECLARED_SYMBOLS = (
     "cfs_cuda_device_count", "cfs_cuda_init", "cfs_cuda_last_error",
-    "cfs_cuda_version", "cfs_cuda_host_alloc", "cfs_cuda_host_free",
+    "cfs_cuda_version", "cfs_cuda_set_option", "cfs_cuda_host_alloc", "cfs_cuda_host_free",
     "cfs_cuda_matrix_create", "cfs_cuda_matrix_create_shard",
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
     "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_timed",
@@ -107,6 +107,7 @@ def lib():
     L.cfs_cuda_version.restype = ctypes.c_char_p
     L.cfs_cuda_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
     L.cfs_cuda_init.argtypes = [ctypes.c_int]
+    L.cfs_cuda_set_option.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
     L.cfs_cuda_host_alloc.restype = vp
     L.cfs_cuda_host_alloc.argtypes = [sz]
     L.cfs_cuda_host_free.argtypes = [vp]
@@ -149,6 +150,10 @@ def device_count():
 
 def init(device=0):
     check(lib().cfs_cuda_init(device))
+
+
+def set_option(key, value):
+    check(lib().cfs_cuda_set_option(key.encode(), int(value)))
 
 
 def _ptr(a):

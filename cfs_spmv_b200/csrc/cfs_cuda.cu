@@ -30,6 +30,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 static int g_device = -1;
+Options g_options;
 
 static int require_device() {
   if (g_device >= 0) {
@@ -81,6 +82,26 @@ extern "C" {
 
 const char *cfs_cuda_last_error(void) { return g_error; }
 const char *cfs_cuda_version(void) { return "cfs-b200 0.1 (sm_100a)"; }
+
+int cfs_cuda_set_option(const char *key, long long value) {
+  if (!key)
+    return CFS_ERR_INVALID;
+  if (!strcmp(key, "spmv_variant") && (value == 1 || value == 2)) {
+    g_options.spmv_variant = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "ctas_per_sm") && value >= 1 && value <= 8) {
+    g_options.ctas_per_sm = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "diag_mode") && value >= 0 && value <= 3) {
+    g_options.diag_mode = (int)value;
+    return CFS_OK;
+  }
+  set_error("cfs_cuda_set_option: unknown key or bad value: %s=%lld", key,
+            value);
+  return CFS_ERR_INVALID;
+}
 
 int cfs_cuda_device_count(int *count) {
   if (!count)
@@ -400,7 +421,7 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
                 m->low_colind.bytes() + m->low_values.bytes() +
                 m->diagonal.bytes() + m->slice_ptr.bytes() +
                 m->vrow_row.bytes() + m->sell_col.bytes() +
-                m->sell_val.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
+                m->sell_val.bytes() + m->tile_info.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
                 m->adj.bytes() + m->color.bytes() + m->color_first.bytes() +
                 m->range_ptr.bytes() + m->part_nranges.bytes() +
                 m->range_start.bytes() + m->range_end.bytes() +

@@ -53,7 +53,13 @@ CFS_GEN_FN double cfs_u01(uint64_t h) {
 /* x vector of the reference's bench: U(0.01, 0.42)
  * (bench/bench_spmv_mmf.cpp:125), but reproducible */
 CFS_GEN_FN double cfs_gen_x(uint64_t seed, int64_t i) {
-  return 0.01 + 0.41 * cfs_u01(cfs_hash3(seed, (uint64_t)i, 0x78ULL));
+  const double u = cfs_u01(cfs_hash3(seed, (uint64_t)i, 0x78ULL));
+#if defined(__CUDA_ARCH__)
+  /* no FMA contraction: bit-identical to the host and numpy versions */
+  return __dadd_rn(0.01, __dmul_rn(0.41, u));
+#else
+  return 0.01 + 0.41 * u;
+#endif
 }
 
 /* BANDED: is (row, row-d) a stored lower entry?  Bernoulli(per_row/16/bw). */

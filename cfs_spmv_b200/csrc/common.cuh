@@ -38,6 +38,18 @@ constexpr int kSliceRows = 32;       // one warp lane per (virtual) row
 constexpr int kMaxChunk = 64;        // longest virtual row; longer rows are split
 constexpr int kVrowCont = 1 << 30;   // flag: virtual row continues an earlier chunk
 constexpr int kVrowRowMask = kVrowCont - 1;
+// Persistent TMA-staged kernel: a tile is up to kTileSlices consecutive slices
+// whose entries (<= kTileSteps slice-steps of 32) are one contiguous piece of
+// the value / index streams, fetched by one bulk copy each.
+constexpr int kTileSlices = 8;
+constexpr int kTileSteps = 128;
+
+struct Options {
+  int spmv_variant = 2;
+  int ctas_per_sm = 2;
+  int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
+};
+extern Options g_options;
 
 template <typename T> struct DevArray {
   T *p = nullptr;
@@ -92,6 +104,8 @@ struct cfs_matrix_s {
   cfsb::DevArray<int32_t> vrow_row;   // nslices*32
   cfsb::DevArray<int32_t> sell_col;   // padded_entries
   cfsb::DevArray<char> sell_val;      // padded_entries
+  int64_t ntiles = 0;
+  cfsb::DevArray<int4> tile_info;     // {first slice, #slices, first step, #steps}
 
   // reference-compatible metadata for P partitions
   int32_t nparts = 1, ncolors = 0, nranges = 0, nblk = 0;

@@ -171,6 +171,45 @@ __global__ void fill_sell_kernel(long long nvrows, long long nslices,
   }
 }
 
+// ---- tiles of the persistent kernel ---------------------------------------
+// Slices are taken in groups of kTileSlices; a group whose slices hold more
+// than kTileSteps slice-steps is cut greedily (a slice never exceeds
+// kMaxChunk <= kTileSteps steps). emit == false counts the tiles of a group.
+template <bool emit>
+__global__ void build_tiles_kernel(long long nslices, long long ngroups,
+                                   const int *__restrict__ slice_ptr,
+                                   int *__restrict__ count,
+                                   const int *__restrict__ offset,
+                                   int4 *__restrict__ tile_info) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= ngroups)
+    return;
+  const long long s0 = g * kTileSlices;
+  const long long s1 = min(s0 + kTileSlices, nslices);
+  int n = 0;
+  int at = emit ? offset[g] : 0;
+  long long first = s0;
+  int steps = 0;
+  for (long long s = s0; s < s1; ++s) {
+    const int w = slice_ptr[s + 1] - slice_ptr[s];
+    if (steps + w > kTileSteps && s > first) {
+      if (emit)
+        tile_info[at + n] = make_int4((int)first, (int)(s - first),
+                                      slice_ptr[first], steps);
+      ++n;
+      first = s;
+      steps = 0;
+    }
+    steps += w;
+  }
+  if (emit)
+    tile_info[at + n] = make_int4((int)first, (int)(s1 - first),
+                                  slice_ptr[first], steps);
+  ++n;
+  if (!emit)
+    count[g] = n;
+}
+
 int exclusive_scan_i32(const int *in, int *out, size_t n, cudaStream_t s) {
   size_t tmp_bytes = 0;
   CFS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out,
@@ -290,6 +329,27 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
           m->sell_col.p, (float *)m->sell_val.p);
   }
   CFS_CUDA_TRY(cudaGetLastError());
+  // tiles of the persistent kernel
+  const long long ngroups = (m->nslices + kTileSlices - 1) / kTileSlices;
+  m->ntiles = 0;
+  if (ngroups > 0) {
+    DevArray<int> tcount, toff;
+    CFS_TRY(tcount.alloc((size_t)ngroups + 1));
+    CFS_TRY(toff.alloc((size_t)ngroups + 1));
+    CFS_CUDA_TRY(cudaMemsetAsync(tcount.p, 0, ((size_t)ngroups + 1) * 4, s));
+    build_tiles_kernel<false><<<blocks_for(ngroups), kThreads, 0, s>>>(
+        m->nslices, ngroups, m->slice_ptr.p, tcount.p, nullptr, nullptr);
+    CFS_CUDA_TRY(cudaGetLastError());
+    CFS_TRY(exclusive_scan_i32(tcount.p, toff.p, (size_t)ngroups + 1, s));
+    int ntiles = 0;
+    CFS_CUDA_TRY(cudaMemcpy(&ntiles, toff.p + ngroups, 4,
+                            cudaMemcpyDeviceToHost));
+    m->ntiles = ntiles;
+    CFS_TRY(m->tile_info.alloc((size_t)ntiles));
+    build_tiles_kernel<true><<<blocks_for(ngroups), kThreads, 0, s>>>(
+        m->nslices, ngroups, m->slice_ptr.p, nullptr, toff.p, m->tile_info.p);
+    CFS_CUDA_TRY(cudaGetLastError());
+  }
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
   return CFS_OK;
 }

@@ -51,6 +51,11 @@ int cfs_cuda_device_count(int *count);
 int cfs_cuda_init(int device);
 const char *cfs_cuda_last_error(void);
 const char *cfs_cuda_version(void);
+/* run-time tunables (the CFS_GPU_* knobs): "spmv_variant" 1 = one warp per
+ * slice with direct loads, 2 = persistent TMA-staged kernel (default);
+ * "ctas_per_sm" for the persistent kernel. Returns CFS_ERR_INVALID for an
+ * unknown key. */
+int cfs_cuda_set_option(const char *key, long long value);
 
 /* ---- allocator: backs internal_alloc / internal_free
  * (include/utils/allocator.hpp:11-12, src/allocator.cpp:8-43).
