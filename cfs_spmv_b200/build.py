@@ -89,7 +89,7 @@ def build_host(force=False):
     if force or _newer(lib, srcs + _headers()):
         subprocess.check_call(
             [HOST_CXX, "-std=c++11", "-O2", "-fPIC", "-shared", "-Wall",
-             "-I" + INCLUDE, "-I" + os.path.join(INCLUDE, "stub_config")]
+             "-I" + INCLUDE]
             + srcs + ["-o", lib, "-L" + LIBDIR, "-lcfs_cuda",
                       "-Wl,-rpath,$ORIGIN"])
     return lib

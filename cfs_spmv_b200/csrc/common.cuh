@@ -45,7 +45,7 @@ constexpr int kTileSlices = 8;
 constexpr int kTileSteps = 128;
 
 struct Options {
-  int spmv_variant = 2;
+  int spmv_variant = 1;
   int ctas_per_sm = 2;
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
