@@ -18,12 +18,28 @@ using namespace cfs::util::runtime;
 using namespace cfs::matrix::sparse;
 using namespace cfs::kernel::sparse;
 
-template <typename V> static bool same(const V *a, const V *b, int n) {
+// double: the reference's element-wise isEqual (test_spmv_mmf.cpp:94-104, which
+// is hard-wired to double). float: normwise 1e-5, the north-star tolerance --
+// element-wise relative checks are meaningless for single precision where
+// y[i] cancels to ~0.
+static bool same(const double *a, const double *b, int n) {
   for (int i = 0; i < n; ++i)
     if (!isEqual(a[i], b[i])) {
       cout << "element " << i << " differs: " << a[i] << " vs " << b[i] << endl;
       return false;
     }
+  return true;
+}
+static bool same(const float *a, const float *b, int n) {
+  double num = 0, den = 0;
+  for (int i = 0; i < n; ++i) {
+    num += ((double)a[i] - b[i]) * ((double)a[i] - b[i]);
+    den += (double)b[i] * b[i];
+  }
+  if (num > 1e-10 * den) {
+    cout << "normwise error " << sqrt(num / den) << endl;
+    return false;
+  }
   return true;
 }
 
