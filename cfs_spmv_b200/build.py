@@ -24,7 +24,9 @@ OBJDIR = os.path.join(ROOT, "build", "obj")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-CUDA_SOURCES = ["cfs_cuda.cu", "preproc.cu", "refmeta.cu", "spmv.cu", "gen.cu"]
+CUDA_SOURCES = ["cfs_cuda.cu", "preproc.cu", "windows.cu", "compress.cu",
+                "refmeta.cu",
+                "spmv.cu", "gen.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", HOST_CXX,

@@ -83,7 +83,10 @@ class MatrixInfo(ctypes.Structure):
                 ("algorithmic_bytes", ctypes.c_int64),
                 ("nvrows", ctypes.c_int64), ("nslices", ctypes.c_int64),
                 ("padded_entries", ctypes.c_int64),
-                ("nconflict_edges", ctypes.c_int64)]
+                ("nconflict_edges", ctypes.c_int64),
+                ("ntiles", ctypes.c_int64), ("far_entries", ctypes.c_int64),
+                ("regular_slices", ctypes.c_int64),
+                ("index_rows", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -86,7 +86,7 @@ const char *cfs_cuda_version(void) { return "cfs-b200 0.1 (sm_100a)"; }
 int cfs_cuda_set_option(const char *key, long long value) {
   if (!key)
     return CFS_ERR_INVALID;
-  if (!strcmp(key, "spmv_variant") && (value == 1 || value == 2)) {
+  if (!strcmp(key, "spmv_variant") && value >= 1 && value <= 5) {
     g_options.spmv_variant = (int)value;
     return CFS_OK;
   }
@@ -331,6 +331,8 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
     }
     CFS_TRY(build_lower(m, m->stream));
     CFS_TRY(build_layout(m, m->stream));
+    CFS_TRY(build_windows(m, m->stream));
+    CFS_TRY(build_compressed_cols(m, m->stream));
     // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
     m->row_split.assign((size_t)nparts + 1, 0);
     if (nparts > 1) {
@@ -398,6 +400,10 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
   info->nslices = m->nslices;
   info->padded_entries = m->padded_entries;
   info->nconflict_edges = m->nedges;
+  info->ntiles = m->ntiles;
+  info->far_entries = m->far_entries;
+  info->regular_slices = m->nregular;
+  info->index_rows = m->ccol_rows;
   if (m->symmetric && m->tuned) {
     // size(), csr_matrix.tpp:191-228 (including its (nrows + 1*nthreads) term)
     int64_t s = ((int64_t)m->nrows + 1LL * m->nparts) * 4;
@@ -421,7 +427,7 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
                 m->low_colind.bytes() + m->low_values.bytes() +
                 m->diagonal.bytes() + m->slice_ptr.bytes() +
                 m->vrow_row.bytes() + m->sell_col.bytes() +
-                m->sell_val.bytes() + m->tile_info.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
+                m->sell_val.bytes() + m->tile_rec.bytes() + m->sell_slot.bytes() + m->ccol.bytes() + m->slice_cptr.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
                 m->adj.bytes() + m->color.bytes() + m->color_first.bytes() +
                 m->range_ptr.bytes() + m->part_nranges.bytes() +
                 m->range_start.bytes() + m->range_end.bytes() +

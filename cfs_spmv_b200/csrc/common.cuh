@@ -35,14 +35,31 @@ constexpr int kBlkFactor = 1 << kBlkBits;
 
 // Execution layout constants
 constexpr int kSliceRows = 32;       // one warp lane per (virtual) row
-constexpr int kMaxChunk = 64;        // longest virtual row; longer rows are split
+constexpr int kMaxChunk = 32;        // longest virtual row; longer rows are split
 constexpr int kVrowCont = 1 << 30;   // flag: virtual row continues an earlier chunk
 constexpr int kVrowRowMask = kVrowCont - 1;
+constexpr int kSliceRegular = 1 << 30; // flag in slice_cptr: regular slice
 // Persistent TMA-staged kernel: a tile is up to kTileSlices consecutive slices
 // whose entries (<= kTileSteps slice-steps of 32) are one contiguous piece of
 // the value / index streams, fetched by one bulk copy each.
-constexpr int kTileSlices = 8;
-constexpr int kTileSteps = 128;
+constexpr int kTileSlices = 4;
+constexpr int kTileSteps = 56;
+
+constexpr int kMaxWindows = 8;   // x / y windows per tile (variant 3)
+constexpr int kWindowBlocks = 28; // 32-column blocks of window space per tile
+
+// Per-tile record, 128 bytes, fetched into shared memory with the tile.
+struct __align__(16) TileRec {
+  int slice_begin, nslices, step_begin, nsteps;
+  int slice_step[8 + 1]; // first step of slice w inside the tile (<= 8 slices)
+  int nwin;              // windows in use (variant 3)
+  int row_lo;            // first row if the tile's rows are consecutive, else -1
+  int pad0;
+  int win_lo[kMaxWindows];                // first global column, multiple of 32
+  unsigned short win_nblk[kMaxWindows];   // 32-column blocks in the window
+  int pad1[4];
+};
+static_assert(sizeof(TileRec) == 128, "TileRec must stay 128 bytes");
 
 struct Options {
   int spmv_variant = 1;
@@ -104,8 +121,17 @@ struct cfs_matrix_s {
   cfsb::DevArray<int32_t> vrow_row;   // nslices*32
   cfsb::DevArray<int32_t> sell_col;   // padded_entries
   cfsb::DevArray<char> sell_val;      // padded_entries
+  // compressed column stream (compress.cu): rows of 32 ints; a regular slice
+  // keeps one row of step bases
+  cfsb::DevArray<int32_t> slice_cptr; // nslices+1; bit 30 = regular
+  cfsb::DevArray<int32_t> ccol;
+  int64_t nregular = 0, ccol_rows = 0;
   int64_t ntiles = 0;
-  cfsb::DevArray<int4> tile_info;     // {first slice, #slices, first step, #steps}
+  cfsb::DevArray<cfsb::TileRec> tile_rec;
+  // variant 3: index stream rewritten to window slots / far codes
+  cfsb::DevArray<int32_t> sell_slot;  // padded_entries
+  cfsb::DevArray<char> zeros;         // clears the y accumulator by bulk copy
+  int64_t far_entries = 0;            // entries left on the global-RED path
 
   // reference-compatible metadata for P partitions
   int32_t nparts = 1, ncolors = 0, nranges = 0, nblk = 0;
@@ -125,6 +151,10 @@ namespace cfsb {
 // preprocessing (preproc.cu)
 int build_lower(cfs_matrix_s *m, cudaStream_t s);
 int build_layout(cfs_matrix_s *m, cudaStream_t s);
+// x / y windows of the tiles (windows.cu)
+int build_windows(cfs_matrix_s *m, cudaStream_t s);
+// index-stream compression of regular slices (compress.cu)
+int build_compressed_cols(cfs_matrix_s *m, cudaStream_t s);
 // reference metadata (refmeta.cu)
 int build_refmeta(cfs_matrix_s *m, cudaStream_t s);
 // kernels (spmv.cu)

@@ -180,7 +180,7 @@ __global__ void build_tiles_kernel(long long nslices, long long ngroups,
                                    const int *__restrict__ slice_ptr,
                                    int *__restrict__ count,
                                    const int *__restrict__ offset,
-                                   int4 *__restrict__ tile_info) {
+                                   TileRec *__restrict__ tile_rec) {
   long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (g >= ngroups)
     return;
@@ -190,22 +190,32 @@ __global__ void build_tiles_kernel(long long nslices, long long ngroups,
   int at = emit ? offset[g] : 0;
   long long first = s0;
   int steps = 0;
+  auto close_tile = [&](long long end) {
+    if (emit) {
+      TileRec r;
+      memset(&r, 0, sizeof(r));
+      r.slice_begin = (int)first;
+      r.nslices = (int)(end - first);
+      r.step_begin = slice_ptr[first];
+      r.nsteps = steps;
+      for (int w = 0; w <= 8; ++w) {
+        const long long sl = first + w < end ? first + w : end;
+        r.slice_step[w] = slice_ptr[sl] - r.step_begin;
+      }
+      tile_rec[at + n] = r;
+    }
+    ++n;
+  };
   for (long long s = s0; s < s1; ++s) {
     const int w = slice_ptr[s + 1] - slice_ptr[s];
     if (steps + w > kTileSteps && s > first) {
-      if (emit)
-        tile_info[at + n] = make_int4((int)first, (int)(s - first),
-                                      slice_ptr[first], steps);
-      ++n;
+      close_tile(s);
       first = s;
       steps = 0;
     }
     steps += w;
   }
-  if (emit)
-    tile_info[at + n] = make_int4((int)first, (int)(s1 - first),
-                                  slice_ptr[first], steps);
-  ++n;
+  close_tile(s1);
   if (!emit)
     count[g] = n;
 }
@@ -252,7 +262,9 @@ int build_lower(cfs_matrix_s *m, cudaStream_t s) {
   CFS_CUDA_TRY(cudaMemcpy(&hdiag, ndiag.p, 8, cudaMemcpyDeviceToHost));
   m->nnz_low = nlow;
   m->nnz_diag = (int64_t)hdiag;
-  m->halo_begin = m->sharded ? (hmin < 0 ? 0 : hmin) : 0;
+  // multiple of 32 columns: keeps every 32-column window block 16-byte
+  // aligned inside the extended vectors (variant 3 bulk copies)
+  m->halo_begin = m->sharded ? ((hmin < 0 ? 0 : hmin) & ~31) : 0;
   CFS_TRY(m->low_colind.alloc((size_t)nlow));
   CFS_TRY(m->low_values.alloc((size_t)nlow * m->vsize()));
   CFS_TRY(m->diagonal.alloc((size_t)n * m->vsize()));
@@ -345,9 +357,9 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
     CFS_CUDA_TRY(cudaMemcpy(&ntiles, toff.p + ngroups, 4,
                             cudaMemcpyDeviceToHost));
     m->ntiles = ntiles;
-    CFS_TRY(m->tile_info.alloc((size_t)ntiles));
+    CFS_TRY(m->tile_rec.alloc((size_t)ntiles));
     build_tiles_kernel<true><<<blocks_for(ngroups), kThreads, 0, s>>>(
-        m->nslices, ngroups, m->slice_ptr.p, nullptr, toff.p, m->tile_info.p);
+        m->nslices, ngroups, m->slice_ptr.p, nullptr, toff.p, m->tile_rec.p);
     CFS_CUDA_TRY(cudaGetLastError());
   }
   CFS_CUDA_TRY(cudaStreamSynchronize(s));

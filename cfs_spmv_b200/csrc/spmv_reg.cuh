@@ -1,0 +1,158 @@
+// spmv_reg.cuh -- variant 5: one warp per slice, compressed column stream,
+// shuffle-merged transposed updates for regular slices.
+//
+// Regular slice (compress.cu): lane l owns row r0+l, step k hits column
+// base_k + l. Only the w bases are read (one 128-byte row instead of w), the
+// value stream is the only thing that still costs 8 bytes/entry of HBM traffic.
+// Steps whose bases are consecutive (base_{k+1} = base_k + 1 -- the three
+// x-neighbours of a stencil) form a CHAIN of length L <= kMaxChain. All
+// transposed updates of a chain land in y[base .. base+32+L-1): lane m collects
+//     S[m] = sum_j p_j[m - j]          (p_j = a_j * x[row], one rotate-shuffle
+//                                       per j)
+// and the L-1 wrapped values go to lanes 0..L-2 as E. One full-warp RED plus one
+// RED with L-1 active lanes replace L full-warp REDs: the GPU restatement of the
+// reference's goal -- fewer, conflict-free writes of the transposed term
+// (csr_matrix.tpp:3005-3013) -- without any shared memory.
+// Irregular slices run the generic loop of variant 1 from the same stream.
+#pragma once
+
+#include "common.cuh"
+#include "spmv_tma.cuh"
+
+namespace cfsb {
+namespace reg {
+
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];"
+               : "=d"(v)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];"
+               : "=f"(v)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];"
+               : "=r"(v)
+               : "l"(p));
+  return v;
+}
+
+constexpr int kThreads = 256;
+constexpr int kMaxChain = 4;
+constexpr int kUnroll = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    sym_spmv_reg_kernel(long long nslices, int row_begin,
+                        const int *__restrict__ slice_ptr,
+                        const int *__restrict__ slice_cptr,
+                        const int *__restrict__ vrow_row,
+                        const int *__restrict__ ccol,
+                        const T *__restrict__ sell_val,
+                        const T *__restrict__ diagonal,
+                        const T *__restrict__ x, T *__restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long s = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
+  if (s >= nslices)
+    return;
+  const int tag = vrow_row[s * kSliceRows + lane];
+  const int p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
+  const int cptr = slice_cptr[s];
+  const bool active = tag >= 0;
+  const int row = tag & kVrowRowMask;
+  T xr = 0, acc = 0;
+  if (active) {
+    xr = x[row];
+    if (!(tag & kVrowCont))
+      acc = diagonal[row - row_begin] * xr;
+  }
+  const T *vp = sell_val + (size_t)p0 * kSliceRows + lane;
+  const int *cp = ccol + (size_t)(cptr & ~kSliceRegular) * kSliceRows + lane;
+  int w = p1 - p0;
+
+  if (cptr & kSliceRegular) {
+    // lane k holds the base column of step k
+    const int base = ld_stream(cp);
+    const int nb = __shfl_down_sync(0xffffffffu, base, 1);
+    const unsigned cont =
+        __ballot_sync(0xffffffffu, lane + 1 < w && nb == base + 1);
+    for (int k = 0; k < w;) {
+      int L = 1;
+      while (L < kMaxChain && ((cont >> (k + L - 1)) & 1u))
+        ++L;
+      const int cbase = __shfl_sync(0xffffffffu, base, k);
+      T a[kMaxChain], xc[kMaxChain];
+#pragma unroll
+      for (int j = 0; j < kMaxChain; ++j) {
+        a[j] = T(0);
+        xc[j] = T(0);
+        if (j < L) {
+          a[j] = ld_stream(vp + (size_t)(k + j) * kSliceRows);
+          xc[j] = x[cbase + lane + j];
+        }
+      }
+      T S = T(0), E = T(0);
+#pragma unroll
+      for (int j = 0; j < kMaxChain; ++j) {
+        if (j < L) { // warp-uniform
+          acc += a[j] * xc[j];
+          const T p = a[j] * xr;
+          const T r = j == 0 ? p : __shfl_sync(0xffffffffu, p, (lane - j) & 31);
+          if (lane >= j)
+            S += r;
+          else
+            E += r;
+        }
+      }
+      tma::red_add(y + cbase + lane, S);
+      if (lane < L - 1)
+        tma::red_add(y + cbase + kSliceRows + lane, E);
+      k += L;
+    }
+  } else {
+    for (; w >= kUnroll; w -= kUnroll) {
+      int c[kUnroll];
+      T a[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        c[u] = ld_stream(cp + u * kSliceRows);
+        a[u] = ld_stream(vp + u * kSliceRows);
+      }
+      T xc[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        xc[u] = c[u] >= 0 ? x[c[u]] : T(0);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (c[u] >= 0) {
+          acc += a[u] * xc[u];
+          tma::red_add(y + c[u], a[u] * xr);
+        }
+      }
+      cp += kUnroll * kSliceRows;
+      vp += kUnroll * kSliceRows;
+    }
+    for (; w > 0; --w) {
+      const int c = ld_stream(cp);
+      const T a = ld_stream(vp);
+      if (c >= 0) {
+        acc += a * x[c];
+        tma::red_add(y + c, a * xr);
+      }
+      cp += kSliceRows;
+      vp += kSliceRows;
+    }
+  }
+  if (active)
+    tma::red_add(y + row, acc);
+}
+
+} // namespace reg
+} // namespace cfsb

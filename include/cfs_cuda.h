@@ -52,7 +52,8 @@ int cfs_cuda_init(int device);
 const char *cfs_cuda_last_error(void);
 const char *cfs_cuda_version(void);
 /* run-time tunables (the CFS_GPU_* knobs): "spmv_variant" 1 = one warp per
- * slice with direct loads, 2 = persistent TMA-staged kernel (default);
+ * slice with direct loads, 2 = persistent TMA-staged kernel, 3 = TMA-staged
+ * with shared-memory x/y windows and bulk reduce-add flush;
  * "ctas_per_sm" for the persistent kernel. Returns CFS_ERR_INVALID for an
  * unknown key. */
 int cfs_cuda_set_option(const char *key, long long value);
@@ -110,6 +111,10 @@ typedef struct cfs_matrix_info {
   int64_t algorithmic_bytes;/* bytes one SpMV must move       */
   int64_t nvrows, nslices, padded_entries; /* execution layout statistics    */
   int64_t nconflict_edges;
+  int64_t ntiles;      /* tiles of the persistent kernels                     */
+  int64_t far_entries; /* entries outside the shared-memory windows (variant 3) */
+  int64_t regular_slices; /* slices whose column stream is compressed to bases */
+  int64_t index_rows;     /* 128-byte rows of the compressed column stream    */
 } cfs_matrix_info;
 
 int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info);

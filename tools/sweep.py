@@ -25,24 +25,35 @@ def main():
     x = capi.gen_device_x(1, 0, N, is_double)
     y = torch.zeros_like(x)
     ref = None
-    configs = [("v1", 1, 2, 0), ("v2", 2, 2, 0)]
+    configs = [("v1", 1, 2, 0), ("v2 ctas=4", 2, 4, 0), ("v3 ctas=2", 3, 2, 0),
+               ("v3 ctas=3", 3, 3, 0), ("v4", 4, 1, 0), ("v5", 5, 1, 0)]
+    print("regular slices %d of %d, index rows %d vs %d" % (
+        inf["regular_slices"], inf["nslices"], inf["index_rows"],
+        inf["padded_entries"] // 32))
+    print("far entries: %d of %d (%.2f%%), tiles %d" % (
+        inf["far_entries"], inf["nnz_low"],
+        100.0 * inf["far_entries"] / max(inf["nnz_low"], 1), inf["ntiles"]))
     if os.environ.get("SWEEP_DIAG"):
         configs += [("v%d noRED" % v, v, 2, 1) for v in (1, 2)]
         configs += [("v%d noGATHER" % v, v, 2, 2) for v in (1, 2)]
         configs += [("v%d stream-only" % v, v, 2, 3) for v in (1, 2)]
+    only = os.environ.get("SWEEP_ONLY")
+    if only:
+        configs = [c for c in configs if c[0].startswith(only)]
+    iters = int(os.environ.get("SWEEP_ITERS", "50"))
     for name, variant, ctas, mode in configs:
         capi.set_option("spmv_variant", variant)
         capi.set_option("ctas_per_sm", ctas)
         capi.set_option("diag_mode", mode)
-        A.spmv_timed(y, x, 5)
-        tot, kern = A.spmv_timed(y, x, 50)
+        A.spmv_timed(y, x, 3)
+        tot, kern = A.spmv_timed(y, x, iters)
         if ref is None:
             ref = y.clone()
         err = (torch.linalg.norm(y - ref) / torch.linalg.norm(ref)).item()
-        us = kern / 50 * 1e3
+        us = kern / iters * 1e3
         print("%-12s kernel %8.1f us  step %8.1f us  %7.1f GB/s alg  "
               "%6.1f GFLOP/s  relerr vs v1 %.2e" % (
-                  name, us, tot / 50 * 1e3,
+                  name, us, tot / iters * 1e3,
                   inf["algorithmic_bytes"] / us / 1e3,
                   2 * inf["nnz_full"] / us / 1e3, err), flush=True)
 
