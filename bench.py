@@ -353,7 +353,8 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "frac_of_8000": achieved / 8000.0,
-                "kernel": "sym_spmv_sell_kernel<double>",
+                "kernel": "sym_spmv_reg_kernel<double> (variant 5: compressed "
+                          "index stream, shuffle-merged REDs)",
                 "kernel_ms": kernel_ms_avg,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "hbm_gbs_whole_step": alg_bytes / (ms_per_step * 1e-3) / 1e9,

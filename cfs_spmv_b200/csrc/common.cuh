@@ -62,7 +62,7 @@ struct __align__(16) TileRec {
 static_assert(sizeof(TileRec) == 128, "TileRec must stay 128 bytes");
 
 struct Options {
-  int spmv_variant = 1;
+  int spmv_variant = 5;
   int ctas_per_sm = 2;
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };

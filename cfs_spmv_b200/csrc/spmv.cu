@@ -231,8 +231,8 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
     variant = 1;
   if (variant == 4)
     return launch_win<T>(m, xb, yb, s);
-  if (variant == 3)
-    return launch_tma<T, true, 0>(m, xb, yb, s);
+  if (variant == 3) // the persistent windowed kernel was retired for 4
+    return launch_win<T>(m, xb, yb, s);
   if (variant == 2) {
     switch (mode) {
     case 1:

@@ -302,3 +302,49 @@ def test_full_size_config2_properties(gpu):
     a, b = torch.dot(x2, y1).item(), torch.dot(x1, y2).item()
     assert abs(a - b) <= 1e-12 * abs(a)
     A.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 4, 5])
+@pytest.mark.parametrize("name,prec", [("lap27_14", "d"), ("lap7_12", "s"),
+                                       ("banded_3000", "d"), ("rmat_9", "d"),
+                                       ("ragged_333", "d"), ("lap27_10", "s")])
+def test_every_kernel_variant_matches_the_reference(gpu, variant, name, prec):
+    """1: warp per slice, 2: persistent TMA-staged, 4: shared-memory x/y
+    windows, 5 (default): compressed index stream + shuffle-merged REDs"""
+    rp, ci, v = cases.matrix(name)
+    dt = cases.dtype_of(prec)
+    x = gen.gen_x(cases.XSEED, len(rp) - 1, dtype=dt)
+    o = oracle.Oracle(rp, ci, v.astype(dt), 1)
+    ref = o.spmv(x)
+    A = capi.Matrix.from_csr(rp, ci, v.astype(dt))
+    A.tune(1)
+    try:
+        capi.set_option("spmv_variant", variant)
+        y = np.full(len(x), -3.0, dtype=dt)
+        for _ in range(2):
+            A.spmv(y, x)
+            assert cases.normwise_rel_err(y, ref) <= cases.TOL[prec]
+    finally:
+        capi.set_option("spmv_variant", 5)
+        A.close()
+
+
+def test_regular_slices_and_windows_are_found(gpu):
+    """layout statistics on a stencil: most slices regular (index stream
+    compressed to bases), few entries outside the windows"""
+    # x-lines of 200 rows: 5 of every 6.25 slices see no grid boundary
+    spec = capi.GenSpec.laplacian(27, 200, 12, 8)
+    rp, ci, v = capi.gen_host_csr(spec)
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(1)
+    inf = A.info()
+    assert inf["regular_slices"] >= 0.6 * inf["nslices"]
+    assert inf["index_rows"] < 0.6 * (inf["padded_entries"] // 32)
+    assert inf["ntiles"] == (inf["nslices"] + 3) // 4
+    # an irregular matrix has none, and still multiplies correctly (above)
+    rp, ci, v = cases.matrix("rmat_9")
+    B = capi.Matrix.from_csr(rp, ci, v)
+    B.tune(1)
+    assert B.info()["regular_slices"] == 0
+    A.close()
+    B.close()
