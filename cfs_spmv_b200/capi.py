@@ -86,7 +86,8 @@ class MatrixInfo(ctypes.Structure):
                 ("nconflict_edges", ctypes.c_int64),
                 ("ntiles", ctypes.c_int64), ("far_entries", ctypes.c_int64),
                 ("regular_slices", ctypes.c_int64),
-                ("index_rows", ctypes.c_int64)]
+                ("index_rows", ctypes.c_int64),
+                ("sort_window", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

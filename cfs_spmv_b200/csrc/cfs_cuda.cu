@@ -94,6 +94,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.ctas_per_sm = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "sort_rows") && (value == 0 || value == 1)) {
+    g_options.sort_rows = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "diag_mode") && value >= 0 && value <= 3) {
     g_options.diag_mode = (int)value;
     return CFS_OK;
@@ -403,6 +407,7 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
   info->ntiles = m->ntiles;
   info->far_entries = m->far_entries;
   info->regular_slices = m->nregular;
+  info->sort_window = m->sort_window;
   info->index_rows = m->ccol_rows;
   if (m->symmetric && m->tuned) {
     // size(), csr_matrix.tpp:191-228 (including its (nrows + 1*nthreads) term)

@@ -64,6 +64,7 @@ static_assert(sizeof(TileRec) == 128, "TileRec must stay 128 bytes");
 struct Options {
   int spmv_variant = 5;
   int ctas_per_sm = 2;
+  int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
 extern Options g_options;
@@ -117,6 +118,7 @@ struct cfs_matrix_s {
 
   // execution layout: sliced ELL over virtual rows
   int64_t nvrows = 0, nslices = 0, padded_entries = 0;
+  int64_t sort_window = 0; // 0: natural order; else rows sorted by length in windows
   cfsb::DevArray<int32_t> slice_ptr;  // nslices+1, units of 32 entries
   cfsb::DevArray<int32_t> vrow_row;   // nslices*32
   cfsb::DevArray<int32_t> sell_col;   // padded_entries

@@ -171,6 +171,39 @@ __global__ void fill_sell_kernel(long long nvrows, long long nslices,
   }
 }
 
+// ---- length sorting of virtual rows ------------------------------------------
+// Ragged matrices waste bandwidth on padding (a slice is as wide as its longest
+// row). Sorting the virtual rows by decreasing length inside windows of
+// `window` rows (SELL-C-sigma) packs rows of similar length together; the window
+// keeps x / y accesses local for banded matrices.
+__global__ void sort_key_kernel(long long nvrows, int window,
+                                const int *__restrict__ vlen,
+                                unsigned *__restrict__ key,
+                                int *__restrict__ idx) {
+  long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= nvrows)
+    return;
+  key[v] = ((unsigned)(v / window) << 6) | (unsigned)(kMaxChunk - vlen[v]);
+  idx[v] = (int)v;
+}
+
+__global__ void permute_vrows_kernel(long long nvrows,
+                                     const int *__restrict__ perm,
+                                     const int *__restrict__ row_in,
+                                     const int *__restrict__ start_in,
+                                     const int *__restrict__ len_in,
+                                     int *__restrict__ row_out,
+                                     int *__restrict__ start_out,
+                                     int *__restrict__ len_out) {
+  long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= nvrows)
+    return;
+  const int p = perm[v];
+  row_out[v] = row_in[p];
+  start_out[v] = start_in[p];
+  len_out[v] = len_in[p];
+}
+
 // ---- tiles of the persistent kernel ---------------------------------------
 // Slices are taken in groups of kTileSlices; a group whose slices hold more
 // than kTileSteps slice-steps is cut greedily (a slice never exceeds
@@ -311,20 +344,64 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
         n, m->row_begin, m->low_rowptr.p, voff.p, m->vrow_row.p, vstart.p,
         vlen.p);
   CFS_CUDA_TRY(cudaGetLastError());
-  // slice widths -> slice_ptr
+  // slice widths -> slice_ptr; if the natural order pads too much, sort the
+  // virtual rows by length (windowed first, globally for heavy skew) and redo
   DevArray<int> width;
   CFS_TRY(width.alloc((size_t)m->nslices + 1));
-  CFS_CUDA_TRY(cudaMemsetAsync(width.p, 0, ((size_t)m->nslices + 1) * 4, s));
-  if (m->nslices > 0)
-    slice_width_kernel<<<blocks_for(nlanes), kThreads, 0, s>>>(
-        m->nvrows, m->nslices, vlen.p, width.p);
-  CFS_CUDA_TRY(cudaGetLastError());
   CFS_TRY(m->slice_ptr.alloc((size_t)m->nslices + 1));
-  CFS_TRY(exclusive_scan_i32(width.p, m->slice_ptr.p, (size_t)m->nslices + 1,
-                             s));
   int total_width = 0;
-  CFS_CUDA_TRY(cudaMemcpy(&total_width, m->slice_ptr.p + m->nslices, 4,
-                          cudaMemcpyDeviceToHost));
+  m->sort_window = 0;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CFS_CUDA_TRY(
+        cudaMemsetAsync(width.p, 0, ((size_t)m->nslices + 1) * 4, s));
+    if (m->nslices > 0)
+      slice_width_kernel<<<blocks_for(nlanes), kThreads, 0, s>>>(
+          m->nvrows, m->nslices, vlen.p, width.p);
+    CFS_CUDA_TRY(cudaGetLastError());
+    CFS_TRY(exclusive_scan_i32(width.p, m->slice_ptr.p,
+                               (size_t)m->nslices + 1, s));
+    CFS_CUDA_TRY(cudaMemcpy(&total_width, m->slice_ptr.p + m->nslices, 4,
+                            cudaMemcpyDeviceToHost));
+    const double padding = m->nnz_low > 0 ? (double)total_width * kSliceRows /
+                                                (double)m->nnz_low
+                                          : 1.0;
+    const double limit = attempt == 0 ? 1.15 : 1.5;
+    if (padding <= limit || attempt == 2 || g_options.sort_rows == 0)
+      break;
+    const long long window = attempt == 0 ? 4096 : (long long)1 << 30;
+    if (nvrows / window >= (1 << 26))
+      break;
+    DevArray<unsigned> key, key_out;
+    DevArray<int> idx, perm, row2, start2, len2;
+    CFS_TRY(key.alloc(nvrows));
+    CFS_TRY(key_out.alloc(nvrows));
+    CFS_TRY(idx.alloc(nvrows));
+    CFS_TRY(perm.alloc(nvrows));
+    CFS_TRY(row2.alloc(nlanes));
+    CFS_TRY(start2.alloc(nlanes));
+    CFS_TRY(len2.alloc(nlanes));
+    sort_key_kernel<<<blocks_for(nvrows), kThreads, 0, s>>>(
+        nvrows, (int)window, vlen.p, key.p, idx.p);
+    size_t tb = 0;
+    CFS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(
+        nullptr, tb, key.p, key_out.p, idx.p, perm.p, nvrows, 0, 32, s));
+    DevArray<char> tmp;
+    CFS_TRY(tmp.alloc(tb));
+    CFS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(
+        tmp.p, tb, key.p, key_out.p, idx.p, perm.p, nvrows, 0, 32, s));
+    permute_vrows_kernel<<<blocks_for(nvrows), kThreads, 0, s>>>(
+        nvrows, perm.p, m->vrow_row.p, vstart.p, vlen.p, row2.p, start2.p,
+        len2.p);
+    CFS_CUDA_TRY(cudaGetLastError());
+    CFS_CUDA_TRY(cudaMemcpyAsync(m->vrow_row.p, row2.p, (size_t)nvrows * 4,
+                                 cudaMemcpyDeviceToDevice, s));
+    CFS_CUDA_TRY(cudaMemcpyAsync(vstart.p, start2.p, (size_t)nvrows * 4,
+                                 cudaMemcpyDeviceToDevice, s));
+    CFS_CUDA_TRY(cudaMemcpyAsync(vlen.p, len2.p, (size_t)nvrows * 4,
+                                 cudaMemcpyDeviceToDevice, s));
+    CFS_CUDA_TRY(cudaStreamSynchronize(s));
+    m->sort_window = window;
+  }
   m->padded_entries = (int64_t)total_width * kSliceRows;
   CFS_TRY(m->sell_col.alloc((size_t)m->padded_entries));
   CFS_TRY(m->sell_val.alloc((size_t)m->padded_entries * m->vsize()));

@@ -220,7 +220,10 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   const int mode = g_options.diag_mode;
   int variant = g_options.spmv_variant;
   // bulk copies of the x / y windows need 16-byte aligned vectors
-  if (variant == 5 && m->ccol.p && mode == 0)
+  // the compressed-index kernel pays off when slices are regular; ragged
+  // matrices run the generic warp-per-slice kernel (more registers, no spills)
+  if (variant == 5 && m->ccol.p && mode == 0 &&
+      m->nregular * 8 >= m->nslices)
     return launch_reg<T>(m, xb, yb, s);
   if (variant == 5)
     variant = 1;

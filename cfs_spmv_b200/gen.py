@@ -113,3 +113,77 @@ def write_mtx(path, rowptr, colind, values, symmetric=True, trailing_newline=Tru
         f.write("\n".join(lines))
         if trailing_newline:
             f.write("\n")
+
+
+# ---------------------------------------------------------------------------
+# device-side R-MAT (torch is only the array library here): bit-identical to
+# rmat() above, but fast enough for BASELINE config 3 (scale 24)
+# ---------------------------------------------------------------------------
+def _t_mix64(z):
+    import torch
+
+    def lsr(v, s):  # logical shift right on int64
+        return (v >> s) & ((1 << (64 - s)) - 1)
+    c1 = -7046029254386353131   # 0x9E3779B97F4A7C15 as int64
+    c2 = -4658895280553007687   # 0xBF58476D1CE4E5B9
+    c3 = -7723592293110705685   # 0x94D049BB133111EB
+    z = z + c1
+    z = (z ^ lsr(z, 30)) * c2
+    z = (z ^ lsr(z, 27)) * c3
+    return z ^ lsr(z, 31)
+
+
+def _t_hash3(seed, a, b):
+    import torch
+    s = _t_mix64(torch.tensor(seed, dtype=torch.int64, device=a.device))
+    return _t_mix64(_t_mix64(s ^ a) ^ b)
+
+
+def _t_u01(h):
+    import torch
+    top = (h >> 11) & ((1 << 53) - 1)
+    return top.to(torch.float64) * (1.0 / 9007199254740992.0)
+
+
+def rmat_torch(scale, edge_factor=8, seed=1, is_double=True,
+               abc=(0.57, 0.19, 0.19), device="cuda", chunk=1 << 24):
+    """same matrix as rmat(), built on `device`; returns torch tensors
+    (rowptr int32, colind int32, values)"""
+    import torch
+    n = 1 << scale
+    m = edge_factor * n
+    a, b, c = abc
+    keys = []
+    for e0 in range(0, m, chunk):
+        e = torch.arange(e0, min(m, e0 + chunk), dtype=torch.int64, device=device)
+        u = torch.zeros_like(e)
+        v = torch.zeros_like(e)
+        for level in range(scale):
+            r = _t_u01(_t_hash3(seed, e, torch.tensor(level, dtype=torch.int64,
+                                                      device=device)))
+            ubit = (r >= a + b).to(torch.int64)
+            vbit = (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
+            u |= ubit << level
+            v |= vbit << level
+        hi = torch.maximum(u, v)
+        lo = torch.minimum(u, v)
+        keep = hi != lo
+        keys.append(torch.unique(hi[keep] * n + lo[keep]))
+    key = torch.unique(torch.cat(keys))
+    del keys
+    hi = key // n
+    lo = key % n
+    val = 2.0 * _t_u01(_t_hash3(seed ^ 0xA5, hi, lo)) - 1.0
+    ar = torch.arange(n, dtype=torch.int64, device=device)
+    rows = torch.cat([hi, lo, ar])
+    cols = torch.cat([lo, hi, ar])
+    vals = torch.cat([val, val, torch.full((n,), 4.0 * edge_factor,
+                                           dtype=torch.float64, device=device)])
+    del hi, lo, val, key
+    order = torch.argsort(rows * n + cols)
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    counts = torch.bincount(rows, minlength=n)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(counts, 0)
+    return (rowptr.to(torch.int32), cols.to(torch.int32),
+            vals if is_double else vals.to(torch.float32))

@@ -115,6 +115,8 @@ typedef struct cfs_matrix_info {
   int64_t far_entries; /* entries outside the shared-memory windows (variant 3) */
   int64_t regular_slices; /* slices whose column stream is compressed to bases */
   int64_t index_rows;     /* 128-byte rows of the compressed column stream    */
+  int64_t sort_window;    /* 0 = natural row order; else rows were sorted by
+                             length inside windows of this many rows          */
 } cfs_matrix_info;
 
 int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info);
