@@ -31,7 +31,8 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_version", "cfs_cuda_set_option", "cfs_cuda_host_alloc", "cfs_cuda_host_free",
     "cfs_cuda_matrix_create", "cfs_cuda_matrix_create_shard",
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
-    "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_timed",
+    "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_halo_async",
+    "cfs_cuda_spmv_timed",
     "cfs_cuda_matrix_export",
     "cfs_gen_host_count", "cfs_gen_host_fill", "cfs_gen_host_x",
     "cfs_cuda_gen_count", "cfs_cuda_gen_fill", "cfs_cuda_gen_x",
@@ -125,6 +126,7 @@ def lib():
     L.cfs_cuda_matrix_info.argtypes = [vp, ctypes.POINTER(MatrixInfo)]
     L.cfs_cuda_spmv.argtypes = [vp, vp, vp]
     L.cfs_cuda_spmv_async.argtypes = [vp, vp, vp, vp]
+    L.cfs_cuda_spmv_halo_async.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
     L.cfs_cuda_spmv_timed.argtypes = [vp, vp, vp, vp, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_float),
                                       ctypes.POINTER(ctypes.c_float)]
@@ -222,6 +224,12 @@ class Matrix:
     def spmv_async(self, y_dev, x_dev, stream=0):
         check(lib().cfs_cuda_spmv_async(self._h, _ptr(y_dev), _ptr(x_dev),
                                         stream))
+
+    def spmv_halo_async(self, y_dev, x_dev, y_lower_base, y_is_zero, stream=0):
+        """SpMV fused with the halo reduction into the GPU below (NVLink)"""
+        check(lib().cfs_cuda_spmv_halo_async(self._h, _ptr(y_dev), _ptr(x_dev),
+                                             y_lower_base, int(y_is_zero),
+                                             stream))
 
     def spmv_timed(self, y_dev, x_dev, iters, stream=0):
         """-> (total_ms, kernel_ms) summed over `iters` SpMVs"""

@@ -454,6 +454,18 @@ int cfs_cuda_spmv_async(cfs_mat_t m, void *y_dev, const void *x_dev,
   return launch_csr_spmv(m, y_dev, x_dev, s);
 }
 
+int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                             void *y_lower_base, int y_is_zero, void *stream) {
+  if (!m || !y_dev || !x_dev)
+    return CFS_ERR_INVALID;
+  if (!m->tuned || !m->symmetric) {
+    set_error("cfs_cuda_spmv_halo_async: needs a tuned symmetric matrix");
+    return CFS_ERR_STATE;
+  }
+  return launch_sym_spmv(m, y_dev, x_dev, (cudaStream_t)stream, nullptr,
+                         nullptr, y_lower_base, y_is_zero != 0);
+}
+
 int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   if (!m || !y || !x)
     return CFS_ERR_INVALID;

@@ -161,9 +161,12 @@ int build_compressed_cols(cfs_matrix_s *m, cudaStream_t s);
 int build_refmeta(cfs_matrix_s *m, cudaStream_t s);
 // kernels (spmv.cu)
 // ev0/ev1 (optional) are recorded directly before/after the kernel launch
+// y_lower_base: virtual base of the y vector of the GPU below (fused halo
+// reduction over NVLink) or nullptr; y_is_zero: the caller cleared y already
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     cudaStream_t s, cudaEvent_t ev0 = nullptr,
-                    cudaEvent_t ev1 = nullptr);
+                    cudaEvent_t ev1 = nullptr, void *y_lower_base = nullptr,
+                    bool y_is_zero = false);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,
                     cudaStream_t s);
 

@@ -59,7 +59,7 @@ constexpr int kUnroll = 4;
 //
 // x and y are "virtual base" pointers: indexed by GLOBAL row/column id (for a
 // shard they point halo_begin elements before the extended local vector).
-template <typename T, int MODE>
+template <typename T, int MODE, bool HALO>
 __global__ void __launch_bounds__(kSpmvThreads)
     sym_spmv_sell_kernel(long long nslices, int row_begin,
                          const int *__restrict__ slice_ptr,
@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kSpmvThreads)
                          const int *__restrict__ sell_col,
                          const T *__restrict__ sell_val,
                          const T *__restrict__ diagonal,
-                         const T *__restrict__ x, T *__restrict__ y) {
+                         const T *__restrict__ x, T *__restrict__ y,
+                         T *__restrict__ y_lower) {
   const int lane = threadIdx.x & 31;
   const long long s =
       (blockIdx.x * (long long)kSpmvThreads + threadIdx.x) >> 5;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kSpmvThreads)
       if (c[u] >= 0) {
         acc += a[u] * xc[u];
         if (!(MODE & 1))
-          tma::red_add(y + c[u], a[u] * xr);
+          tma::y_add<HALO>(y, y_lower, row_begin, c[u], a[u] * xr);
         else
           acc += a[u] * xr;
       }
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kSpmvThreads)
     if (c >= 0) {
       acc += a * ((MODE & 2) ? xr : x[c]);
       if (!(MODE & 1))
-        tma::red_add(y + c, a * xr);
+        tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
     }
     cp += kSliceRows;
     vp += kSliceRows;
@@ -154,12 +155,18 @@ __global__ void __launch_bounds__(kSpmvThreads)
 constexpr int kStagesPlain = 2, kStagesWindows = 3;
 
 template <typename T, int MODE>
-void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
+void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
+                 cudaStream_t s) {
   const unsigned grid =
       (unsigned)((m->nslices * 32 + kSpmvThreads - 1) / kSpmvThreads);
-  sym_spmv_sell_kernel<T, MODE><<<grid, kSpmvThreads, 0, s>>>(
-      m->nslices, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
-      (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb);
+  if (y_lower)
+    sym_spmv_sell_kernel<T, MODE, true><<<grid, kSpmvThreads, 0, s>>>(
+        m->nslices, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
+        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower);
+  else
+    sym_spmv_sell_kernel<T, MODE, false><<<grid, kSpmvThreads, 0, s>>>(
+        m->nslices, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
+        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr);
 }
 
 template <typename T, bool WINDOWS, int MODE>
@@ -195,12 +202,20 @@ int launch_tma(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 }
 
 template <typename T>
-int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
+int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
+               cudaStream_t s) {
   const unsigned grid =
       (unsigned)((m->nslices * 32 + reg::kThreads - 1) / reg::kThreads);
-  reg::sym_spmv_reg_kernel<T><<<grid, reg::kThreads, 0, s>>>(
-      m->nslices, m->row_begin, m->slice_ptr.p, m->slice_cptr.p, m->vrow_row.p,
-      m->ccol.p, (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb);
+  if (y_lower)
+    reg::sym_spmv_reg_kernel<T, true><<<grid, reg::kThreads, 0, s>>>(
+        m->nslices, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
+        m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
+        (const T *)m->diagonal.p, xb, yb, y_lower);
+  else
+    reg::sym_spmv_reg_kernel<T, false><<<grid, reg::kThreads, 0, s>>>(
+        m->nslices, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
+        m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
+        (const T *)m->diagonal.p, xb, yb, nullptr);
   return CFS_OK;
 }
 
@@ -214,18 +229,21 @@ int launch_win(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 
 template <typename T>
 int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
-                     cudaStream_t s) {
+                     void *y_lower_base, cudaStream_t s) {
   const T *xb = (const T *)x_ext - m->halo_begin;
   T *yb = (T *)y_ext - m->halo_begin;
+  T *yl = (T *)y_lower_base;
   const int mode = g_options.diag_mode;
   int variant = g_options.spmv_variant;
+  if (yl && variant != 1)
+    variant = 5; // the fused halo path exists in the register kernels
   // bulk copies of the x / y windows need 16-byte aligned vectors
   // the compressed-index kernel pays off when slices are regular; ragged
   // matrices run the generic warp-per-slice kernel (more registers, no spills)
   if (variant == 5 && m->ccol.p && mode == 0 &&
       m->nregular * 8 >= m->nslices)
-    return launch_reg<T>(m, xb, yb, s);
-  if (variant == 5)
+    return launch_reg<T>(m, xb, yb, yl, s);
+  if (variant == 5 || yl)
     variant = 1;
   if (variant >= 3 &&
       (!m->sell_slot.p || (((uintptr_t)x_ext | (uintptr_t)y_ext) & 15)))
@@ -250,16 +268,16 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   }
   switch (mode) {
   case 1:
-    launch_sell<T, 1>(m, xb, yb, s);
+    launch_sell<T, 1>(m, xb, yb, yl, s);
     break;
   case 2:
-    launch_sell<T, 2>(m, xb, yb, s);
+    launch_sell<T, 2>(m, xb, yb, yl, s);
     break;
   case 3:
-    launch_sell<T, 3>(m, xb, yb, s);
+    launch_sell<T, 3>(m, xb, yb, yl, s);
     break;
   default:
-    launch_sell<T, 0>(m, xb, yb, s);
+    launch_sell<T, 0>(m, xb, yb, yl, s);
     break;
   }
   return CFS_OK;
@@ -268,16 +286,19 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
 } // namespace
 
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
-                    cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
+                    cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1,
+                    void *y_lower_base, bool y_is_zero) {
   const size_t vs = m->vsize();
   const size_t ext_len = (size_t)(m->row_begin + m->nrows - m->halo_begin);
-  CFS_CUDA_TRY(cudaMemsetAsync(y_ext, 0, ext_len * vs, s));
+  if (!y_is_zero)
+    CFS_CUDA_TRY(cudaMemsetAsync(y_ext, 0, ext_len * vs, s));
   if (m->nslices == 0)
     return CFS_OK;
   if (ev0)
     CFS_CUDA_TRY(cudaEventRecord(ev0, s));
-  CFS_TRY(m->is_double ? launch_sym_typed<double>(m, y_ext, x_ext, s)
-                       : launch_sym_typed<float>(m, y_ext, x_ext, s));
+  CFS_TRY(m->is_double
+              ? launch_sym_typed<double>(m, y_ext, x_ext, y_lower_base, s)
+              : launch_sym_typed<float>(m, y_ext, x_ext, y_lower_base, s));
   CFS_CUDA_TRY(cudaGetLastError());
   if (ev1)
     CFS_CUDA_TRY(cudaEventRecord(ev1, s));

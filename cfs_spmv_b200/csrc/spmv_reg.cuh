@@ -50,7 +50,7 @@ constexpr int kUnroll = 4;
 
 // 8 CTAs of 256 threads per SM: the kernel is latency-bound, occupancy wins over
 // registers (measured: 275 us at 40 registers, 239 us at 32)
-template <typename T>
+template <typename T, bool HALO>
 __global__ void __launch_bounds__(kThreads, 8)
     sym_spmv_reg_kernel(long long nslices, int row_begin,
                         const int *__restrict__ slice_ptr,
@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(kThreads, 8)
                         const int *__restrict__ ccol,
                         const T *__restrict__ sell_val,
                         const T *__restrict__ diagonal,
-                        const T *__restrict__ x, T *__restrict__ y) {
+                        const T *__restrict__ x, T *__restrict__ y,
+                        T *__restrict__ y_lower) {
   const int lane = threadIdx.x & 31;
   const long long s = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
   if (s >= nslices)
@@ -113,9 +114,15 @@ __global__ void __launch_bounds__(kThreads, 8)
             E += r;
         }
       }
-      tma::red_add(y + cbase + lane, S);
-      if (lane < L - 1)
-        tma::red_add(y + cbase + kSliceRows + lane, E);
+      if (HALO && cbase < row_begin) { // warp-uniform: chain reaches the halo
+        tma::y_add<true>(y, y_lower, row_begin, cbase + lane, S);
+        if (lane < L - 1)
+          tma::y_add<true>(y, y_lower, row_begin, cbase + kSliceRows + lane, E);
+      } else {
+        tma::red_add(y + cbase + lane, S);
+        if (lane < L - 1)
+          tma::red_add(y + cbase + kSliceRows + lane, E);
+      }
       k += L;
     }
   } else {
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 8)
       for (int u = 0; u < kUnroll; ++u) {
         if (c[u] >= 0) {
           acc += a[u] * xc[u];
-          tma::red_add(y + c[u], a[u] * xr);
+          tma::y_add<HALO>(y, y_lower, row_begin, c[u], a[u] * xr);
         }
       }
       cp += kUnroll * kSliceRows;
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 8)
       const T a = ld_stream(vp);
       if (c >= 0) {
         acc += a * x[c];
-        tma::red_add(y + c, a * xr);
+        tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
       }
       cp += kSliceRows;
       vp += kSliceRows;

@@ -75,6 +75,29 @@ __device__ __forceinline__ void red_add(float *p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// Remote reduction: the target lives in a peer GPU's memory (NVLink, mapped
+// through symmetric memory), so the reduction is issued at system scope.
+__device__ __forceinline__ void red_add_sys(double *p, double v) {
+  asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p), "d"(v)
+               : "memory");
+}
+__device__ __forceinline__ void red_add_sys(float *p, float v) {
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v)
+               : "memory");
+}
+// y[col] += v. With HALO the columns below row_begin belong to the row block of
+// the GPU below: they are reduced straight into ITS y over NVLink (y_lower is
+// that vector's virtual base pointer), fused into the SpMV kernel instead of a
+// separate exchange step.
+template <bool HALO, typename T>
+__device__ __forceinline__ void y_add(T *y, T *y_lower, int row_begin, int col,
+                                      T v) {
+  if (HALO && col < row_begin)
+    red_add_sys(y_lower + col, v);
+  else
+    red_add(y + col, v);
+}
+
 constexpr int kWinSlots = kWindowBlocks * 32;
 constexpr int kTileRows = kTileSlices * kSliceRows;
 

@@ -106,6 +106,57 @@ class HaloExchanger:
             y_ext[self._sl(lo, hi)] += buf
 
 
+class P2PHalo:
+    """Halo handling over peer memory (NVLink) instead of NCCL messages.
+
+    x_ext / y_ext of every rank live in symmetric memory
+    (torch.distributed._symmetric_memory: plumbing that maps each rank's buffer
+    into the others and provides a device-side barrier). Per step:
+      clear y -> barrier -> pull the x halo from the GPU below (peer load) ->
+      SpMV kernel that reduces its halo contributions straight into the y of
+      the GPU below (cfs_cuda_spmv_halo_async) -> barrier.
+    Needs every halo to lie inside the row block of ONE lower neighbour (true
+    for stencil and banded matrices)."""
+
+    def __init__(self, ranges, rank, dtype, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = rank, len(ranges)
+        self.h, self.b, self.e = ranges[rank]
+        for g in range(1, self.world):
+            if ranges[g][0] < ranges[g - 1][1]:
+                raise RuntimeError("halo of rank %d spans more than one "
+                                   "neighbour" % g)
+        max_len = max(e - h for h, b, e in ranges)
+        self.x_sym = symm_mem.empty(max_len, dtype=dtype, device=device)
+        self.y_sym = symm_mem.empty(max_len, dtype=dtype, device=device)
+        self.hx = symm_mem.rendezvous(self.x_sym, dist.group.WORLD)
+        self.hy = symm_mem.rendezvous(self.y_sym, dist.group.WORLD)
+        n = self.e - self.h
+        self.x_ext = self.x_sym[:n]
+        self.y_ext = self.y_sym[:n]
+        self.y_lower_base = None
+        self.x_peer = None
+        self.nhalo = self.b - self.h
+        if rank > 0 and self.nhalo > 0:
+            ph = ranges[rank - 1][0]
+            item = self.x_sym.element_size()
+            self.y_lower_base = self.hy.buffer_ptrs[rank - 1] - ph * item
+            peer_x = self.hx.get_buffer(rank - 1, (max_len,), dtype)
+            self.x_peer = peer_x[self.h - ph:self.b - ph]
+        self.bytes_per_step = 2 * self.nhalo * self.x_sym.element_size()
+
+    def step(self, matrix, stream):
+        self.y_ext.zero_()
+        self.hy.barrier()              # every y is clear, every x is final
+        if self.x_peer is not None:
+            self.x_ext[:self.nhalo].copy_(self.x_peer)
+        matrix.spmv_halo_async(self.y_ext, self.x_ext, self.y_lower_base, True,
+                               stream)
+        self.hy.barrier()              # all halo reductions have landed
+
+
 class ShardedSpMV:
     """One rank's share of y = A*x for a generated matrix (bench / tests)."""
 
@@ -136,21 +187,53 @@ class ShardedSpMV:
             ranges = [tuple(int(v) for v in t.tolist()) for t in allr]
         else:
             ranges = [(h, b, e)]
-        self.x_ext = capi.gen_device_x(xseed, h, e, is_double)
-        # the halo part of x is (re)filled by exchange_x every step
-        self.y_ext = torch.zeros_like(self.x_ext)
+        x_gen = capi.gen_device_x(xseed, h, e, is_double)
+        self.p2p = None
+        import os
+        mode = os.environ.get("CFS_GPU_HALO", "p2p" if world > 1 else "none")
+        if world > 1 and mode == "p2p":
+            try:
+                self.p2p = P2PHalo(ranges, rank, x_gen.dtype, x_gen.device)
+            except Exception as exc:  # no peer access / halo too wide
+                if rank == 0:
+                    print("P2P halo unavailable (%s): using NCCL messages" % exc,
+                          flush=True)
+                self.p2p = None
+            ok = torch.tensor([1 if self.p2p is not None else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                self.p2p = None
+        if self.p2p is not None:
+            self.x_ext, self.y_ext = self.p2p.x_ext, self.p2p.y_ext
+            self.x_ext.copy_(x_gen)
+            self.y_ext.zero_()
+        else:
+            self.x_ext = x_gen
+            # the halo part of x is (re)filled by exchange_x every step
+            self.y_ext = torch.zeros_like(self.x_ext)
         self.halo = HaloExchanger(ranges, rank, self.x_ext)
         nh = len(self.halo.recv_x) + len(self.halo.send_x)
-        self.exchange_desc = (
-            "none (single GPU)" if world == 1 else
-            "NCCL P2P per step: x halo down-up, y halo strip add; "
-            "%d neighbour segments, %d bytes on rank %d" % (
-                nh, self.halo.bytes_per_step, rank))
+        if world == 1:
+            self.exchange_desc = "none (single GPU)"
+        elif self.p2p is not None:
+            self.exchange_desc = (
+                "fused over NVLink peer memory: x halo pulled from the GPU "
+                "below, y halo contributions reduced by the SpMV kernel straight "
+                "into its y (RED.sys); 2 device barriers per step; %d bytes on "
+                "rank %d" % (self.p2p.bytes_per_step, rank))
+        else:
+            self.exchange_desc = (
+                "NCCL P2P per step: x halo down-up, y halo strip add; "
+                "%d neighbour segments, %d bytes on rank %d" % (
+                    nh, self.halo.bytes_per_step, rank))
         self._host = None
 
     def step(self):
         import torch
         s = torch.cuda.current_stream().cuda_stream
+        if self.p2p is not None:
+            self.p2p.step(self.matrix, s)
+            return
         self.halo.exchange_x(self.x_ext)
         self.matrix.spmv_async(self.y_ext, self.x_ext, s)
         self.halo.reduce_y(self.y_ext)
@@ -192,8 +275,11 @@ class ShardedSpMV:
 
         def one():
             self.x_ext.copy_(x_host, non_blocking=True)
-            self.matrix.spmv_async(self.y_ext, self.x_ext, s.cuda_stream)
-            self.halo.reduce_y(self.y_ext)
+            if self.p2p is not None:
+                self.p2p.step(self.matrix, s.cuda_stream)
+            else:
+                self.matrix.spmv_async(self.y_ext, self.x_ext, s.cuda_stream)
+                self.halo.reduce_y(self.y_ext)
             y_host.copy_(self.y_owned(), non_blocking=True)
             s.synchronize()
 

@@ -134,6 +134,18 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x);
 int cfs_cuda_spmv_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                         void *stream);
 
+/* Multi-GPU SpMV fused with its exchange step. The transposed contributions to
+ * columns below row_begin -- the reference's "direct conflicts" with the
+ * partitions below (csr_matrix.tpp:1441-1451) -- are reduced by the kernel
+ * straight into the y vector of the GPU that owns those rows, over NVLink:
+ * y_lower_base is that (peer-mapped, e.g. symmetric-memory) vector's address
+ * minus its halo_begin elements, so that y_lower_base[col] is y[col] there.
+ * Requires that this shard's halo lies inside the row block of ONE GPU below.
+ * The caller zeroes y on every GPU and synchronises the GPUs before and after
+ * (y_is_zero != 0 skips the internal memset). */
+int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                             void *y_lower_base, int y_is_zero, void *stream);
+
 /* Measurement aid for bench.py (bench_spmv_mmf.cpp:162-167 times the same
  * loop with omp_get_wtime): runs `iters` SpMVs on `stream` and returns the
  * summed device time of the SpMV KERNEL alone (kernel_ms, CUDA events placed

@@ -25,6 +25,7 @@ def main():
     capi.init(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures = 0
+    mode = os.environ.get("CFS_GPU_HALO", "p2p")
     for spec, dbl in ((capi.GenSpec.laplacian(27, 40, 40, 16 * world), True),
                       (capi.GenSpec.laplacian(7, 33, 17, 24 * world), False),
                       (capi.GenSpec.banded(20000 * world, 700, 152, 3), True)):
@@ -44,8 +45,9 @@ def main():
             y = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])])
             err = np.linalg.norm(y.astype(np.float64) - ref) / np.linalg.norm(ref)
             ok = err <= (1e-12 if dbl else 1e-5)
-            print("multi-gpu world=%d kind=%d %s err=%.3e %s" % (
-                world, spec.kind, "f64" if dbl else "f32", err,
+            print("multi-gpu world=%d halo=%s(%s) kind=%d %s err=%.3e %s" % (
+                world, mode, "p2p" if op.p2p is not None else "nccl",
+                spec.kind, "f64" if dbl else "f32", err,
                 "OK" if ok else "FAIL"), flush=True)
             failures += not ok
     dist.barrier()

@@ -12,8 +12,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_spmv_matches_oracle(gpu, world):
+def test_sharded_spmv_matches_oracle(gpu, world, halo):
     if gpu.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     s = socket.socket()
@@ -25,6 +26,7 @@ def test_sharded_spmv_matches_oracle(gpu, world):
          "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
          "--master-port", str(port),
          os.path.join(ROOT, "tests", "multi_gpu_worker.py")],
-        capture_output=True, text=True, timeout=600)
+        capture_output=True, text=True, timeout=600,
+        env=dict(os.environ, CFS_GPU_HALO=halo))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" OK") == 3 and "FAIL" not in r.stdout
