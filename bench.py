@@ -363,7 +363,8 @@ def main():
                 "value": 2.0 * nnz_full * 1e-9 / (e2e_t.item() / e2e_steps * 1e-3),
                 "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
-                "path": "cfs_cuda_spmv(host y, host x): pinned H2D + kernel + D2H"
+                "path": "cfs_cuda_spmv(host y, host x): pinned H2D, kernel and D2H "
+                        "overlapped in 16 row chunks"
                         if world == 1 else
                         "pinned H2D of x shard+halo, kernel, NCCL y halo, D2H",
             },

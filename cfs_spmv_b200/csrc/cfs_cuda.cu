@@ -98,6 +98,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.sort_rows = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "pipeline") && (value == 0 || value == 1)) {
+    g_options.pipeline = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "diag_mode") && value >= 0 && value <= 3) {
     g_options.diag_mode = (int)value;
     return CFS_OK;
@@ -337,6 +341,7 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
     CFS_TRY(build_layout(m, m->stream));
     CFS_TRY(build_windows(m, m->stream));
     CFS_TRY(build_compressed_cols(m, m->stream));
+    CFS_TRY(build_pipeline_plan(m, m->stream));
     // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
     m->row_split.assign((size_t)nparts + 1, 0);
     if (nparts > 1) {
@@ -376,6 +381,14 @@ void cfs_cuda_matrix_destroy(cfs_mat_t m) {
   if (!m)
     return;
   cudaSetDevice(m->device);
+  for (cudaEvent_t e : m->ev_x)
+    cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_k)
+    cudaEventDestroy(e);
+  if (m->h2d_stream)
+    cudaStreamDestroy(m->h2d_stream);
+  if (m->d2h_stream)
+    cudaStreamDestroy(m->d2h_stream);
   if (m->stream)
     cudaStreamDestroy(m->stream);
   delete m;
@@ -466,6 +479,61 @@ int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                          nullptr, y_lower_base, y_is_zero != 0);
 }
 
+// Host vectors in, host vectors out: H2D of x, the kernel and D2H of y overlap
+// chunk by chunk (see cfs_matrix_s::Chunk). Three streams, events between them.
+static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x) {
+  const size_t vs = m->vsize();
+  const size_t K = m->chunks.size();
+  if (!m->h2d_stream) {
+    CFS_CUDA_TRY(cudaStreamCreateWithFlags(&m->h2d_stream,
+                                           cudaStreamNonBlocking));
+    CFS_CUDA_TRY(cudaStreamCreateWithFlags(&m->d2h_stream,
+                                           cudaStreamNonBlocking));
+    m->ev_x.resize(K);
+    m->ev_k.resize(K);
+    for (size_t c = 0; c < K; ++c) {
+      CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_x[c],
+                                            cudaEventDisableTiming));
+      CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_k[c],
+                                            cudaEventDisableTiming));
+    }
+  }
+  if (!m->stage_x.p)
+    CFS_TRY(m->stage_x.alloc((size_t)m->ncols * vs));
+  if (!m->stage_y.p)
+    CFS_TRY(m->stage_y.alloc((size_t)m->nrows * vs));
+  char *xd = m->stage_x.p, *yd = m->stage_y.p;
+  CFS_CUDA_TRY(cudaMemsetAsync(yd, 0, (size_t)m->nrows * vs, m->stream));
+  size_t next_out = 0;
+  for (size_t c = 0; c < K; ++c) {
+    const cfs_matrix_s::Chunk &ch = m->chunks[c];
+    const size_t xo = (size_t)ch.row0 * vs;
+    // the last chunk also carries the columns beyond the last row (none for a
+    // square matrix, kept for safety)
+    const size_t xe = (c + 1 == K ? (size_t)m->ncols : (size_t)ch.row1) * vs;
+    if (xe > xo)
+      CFS_CUDA_TRY(cudaMemcpyAsync(xd + xo, (const char *)x + xo, xe - xo,
+                                   cudaMemcpyHostToDevice, m->h2d_stream));
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_x[c], m->h2d_stream));
+    CFS_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_x[c], 0));
+    CFS_TRY(launch_sym_spmv(m, yd, xd, m->stream, nullptr, nullptr, nullptr,
+                            true, ch.slice0, ch.slice1));
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_k[c], m->stream));
+    while (next_out < K && m->chunks[next_out].final_after <= (int)c) {
+      const cfs_matrix_s::Chunk &o = m->chunks[next_out];
+      const size_t yo = (size_t)o.row0 * vs, ye = (size_t)o.row1 * vs;
+      CFS_CUDA_TRY(cudaStreamWaitEvent(m->d2h_stream, m->ev_k[c], 0));
+      if (ye > yo)
+        CFS_CUDA_TRY(cudaMemcpyAsync((char *)y + yo, yd + yo, ye - yo,
+                                     cudaMemcpyDeviceToHost, m->d2h_stream));
+      ++next_out;
+    }
+  }
+  CFS_CUDA_TRY(cudaStreamSynchronize(m->d2h_stream));
+  CFS_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return CFS_OK;
+}
+
 int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   if (!m || !y || !x)
     return CFS_ERR_INVALID;
@@ -482,6 +550,9 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   PtrKind kx, ky;
   classify(x, &kx);
   classify(y, &ky);
+  if (kx == kPtrHost && ky == kPtrHost && m->symmetric && !m->chunks.empty() &&
+      g_options.pipeline)
+    return spmv_host_pipelined(m, y, x);
   const void *xd = x;
   void *yd = y;
   if (kx == kPtrHost) {

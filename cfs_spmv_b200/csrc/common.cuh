@@ -64,6 +64,7 @@ static_assert(sizeof(TileRec) == 128, "TileRec must stay 128 bytes");
 struct Options {
   int spmv_variant = 5;
   int ctas_per_sm = 2;
+  int pipeline = 1;  // overlap H2D / kernel / D2H in cfs_cuda_spmv(host, host)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
@@ -146,6 +147,18 @@ struct cfs_matrix_s {
   // staging for the synchronous host-pointer entry point
   cfsb::DevArray<char> stage_x, stage_y;
   cudaStream_t stream = nullptr;
+  // Host-vector pipeline (cfs_cuda_spmv with host x and y): the lower triangle
+  // only looks DOWN, so a chunk of rows can run as soon as x up to its last row
+  // has arrived, and its y rows are final once every chunk that reaches down
+  // into them is done: H2D, kernel and D2H overlap chunk by chunk.
+  struct Chunk {
+    long long slice0, slice1;
+    int row0, row1;       // rows whose y this chunk owns
+    int final_after;      // index of the last chunk that adds into these rows
+  };
+  std::vector<Chunk> chunks;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> ev_x, ev_k;
 };
 
 namespace cfsb {
@@ -166,7 +179,10 @@ int build_refmeta(cfs_matrix_s *m, cudaStream_t s);
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     cudaStream_t s, cudaEvent_t ev0 = nullptr,
                     cudaEvent_t ev1 = nullptr, void *y_lower_base = nullptr,
-                    bool y_is_zero = false);
+                    bool y_is_zero = false, long long slice0 = 0,
+                    long long slice1 = -1);
+// host-vector pipeline plan (preproc.cu)
+int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,
                     cudaStream_t s);
 

@@ -443,4 +443,79 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
   return CFS_OK;
 }
 
+namespace {
+// min column of the entries of slices [slice0, slice1)
+__global__ void chunk_min_col_kernel(const int *__restrict__ slice_ptr,
+                                     const int *__restrict__ sell_col,
+                                     long long slice0, long long slice1,
+                                     int *__restrict__ out) {
+  const size_t begin = (size_t)slice_ptr[slice0] * kSliceRows;
+  const size_t end = (size_t)slice_ptr[slice1] * kSliceRows;
+  int lo = INT_MAX;
+  for (size_t i = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+       i < end; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = sell_col[i];
+    if (c >= 0)
+      lo = min(lo, c);
+  }
+  typedef cub::BlockReduce<int, kThreads> Reduce;
+  __shared__ typename Reduce::TempStorage tmp;
+  lo = Reduce(tmp).Reduce(lo, cub::Min());
+  if (threadIdx.x == 0)
+    atomicMin(out, lo);
+}
+} // namespace
+
+// Chunks of consecutive slices for the host-vector pipeline of cfs_cuda_spmv.
+// Only for layouts in natural row order on an unsharded matrix.
+int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
+  m->chunks.clear();
+  if (m->sharded || m->sort_window != 0 || m->nslices < 4096)
+    return CFS_OK;
+  const int K = 16;
+  std::vector<long long> cut(K + 1);
+  for (int c = 0; c <= K; ++c)
+    cut[c] = m->nslices * c / K;
+  // first row of each chunk = row tag of its first lane
+  std::vector<int> row0(K + 1, m->nrows);
+  for (int c = 0; c < K; ++c) {
+    int tag = 0;
+    CFS_CUDA_TRY(cudaMemcpy(&tag, m->vrow_row.p + cut[c] * kSliceRows, 4,
+                            cudaMemcpyDeviceToHost));
+    if (tag < 0)
+      return CFS_OK;
+    row0[c] = tag & kVrowRowMask;
+  }
+  DevArray<int> lo_dev;
+  CFS_TRY(lo_dev.alloc(K));
+  std::vector<int> init(K, INT_MAX), lo(K);
+  CFS_CUDA_TRY(cudaMemcpyAsync(lo_dev.p, init.data(), K * 4,
+                               cudaMemcpyHostToDevice, s));
+  for (int c = 0; c < K; ++c)
+    chunk_min_col_kernel<<<256, kThreads, 0, s>>>(m->slice_ptr.p, m->sell_col.p,
+                                                 cut[c], cut[c + 1],
+                                                 lo_dev.p + c);
+  CFS_CUDA_TRY(cudaGetLastError());
+  CFS_CUDA_TRY(cudaMemcpyAsync(lo.data(), lo_dev.p, K * 4,
+                               cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  for (int c = 0; c < K; ++c) {
+    if (row0[c + 1] < row0[c])
+      return CFS_OK; // not in row order after all
+    cfs_matrix_s::Chunk ch;
+    ch.slice0 = cut[c];
+    ch.slice1 = cut[c + 1];
+    ch.row0 = row0[c];
+    ch.row1 = row0[c + 1];
+    ch.final_after = c;
+    m->chunks.push_back(ch);
+  }
+  // y rows of chunk d are final after the last chunk that reaches below row1
+  for (int d = 0; d < K; ++d)
+    for (int c = d + 1; c < K; ++c)
+      if (lo[c] < m->chunks[d].row1)
+        m->chunks[d].final_after = c;
+  return CFS_OK;
+}
+
 } // namespace cfsb

@@ -61,7 +61,8 @@ constexpr int kUnroll = 4;
 // shard they point halo_begin elements before the extended local vector).
 template <typename T, int MODE, bool HALO>
 __global__ void __launch_bounds__(kSpmvThreads)
-    sym_spmv_sell_kernel(long long nslices, int row_begin,
+    sym_spmv_sell_kernel(long long slice_begin, long long slice_end,
+                         int row_begin,
                          const int *__restrict__ slice_ptr,
                          const int *__restrict__ vrow_row,
                          const int *__restrict__ sell_col,
@@ -71,8 +72,8 @@ __global__ void __launch_bounds__(kSpmvThreads)
                          T *__restrict__ y_lower) {
   const int lane = threadIdx.x & 31;
   const long long s =
-      (blockIdx.x * (long long)kSpmvThreads + threadIdx.x) >> 5;
-  if (s >= nslices)
+      slice_begin + ((blockIdx.x * (long long)kSpmvThreads + threadIdx.x) >> 5);
+  if (s >= slice_end)
     return;
   const int tag = vrow_row[s * kSliceRows + lane];
   const bool active = tag >= 0;
@@ -156,16 +157,16 @@ constexpr int kStagesPlain = 2, kStagesWindows = 3;
 
 template <typename T, int MODE>
 void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-                 cudaStream_t s) {
+                 cudaStream_t s, long long s0, long long s1) {
   const unsigned grid =
-      (unsigned)((m->nslices * 32 + kSpmvThreads - 1) / kSpmvThreads);
+      (unsigned)(((s1 - s0) * 32 + kSpmvThreads - 1) / kSpmvThreads);
   if (y_lower)
     sym_spmv_sell_kernel<T, MODE, true><<<grid, kSpmvThreads, 0, s>>>(
-        m->nslices, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
+        s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
         (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower);
   else
     sym_spmv_sell_kernel<T, MODE, false><<<grid, kSpmvThreads, 0, s>>>(
-        m->nslices, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
+        s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
         (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr);
 }
 
@@ -203,17 +204,17 @@ int launch_tma(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 
 template <typename T>
 int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-               cudaStream_t s) {
+               cudaStream_t s, long long s0, long long s1) {
   const unsigned grid =
-      (unsigned)((m->nslices * 32 + reg::kThreads - 1) / reg::kThreads);
+      (unsigned)(((s1 - s0) * 32 + reg::kThreads - 1) / reg::kThreads);
   if (y_lower)
     reg::sym_spmv_reg_kernel<T, true><<<grid, reg::kThreads, 0, s>>>(
-        m->nslices, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
+        s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
         m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
         (const T *)m->diagonal.p, xb, yb, y_lower);
   else
     reg::sym_spmv_reg_kernel<T, false><<<grid, reg::kThreads, 0, s>>>(
-        m->nslices, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
+        s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
         m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
         (const T *)m->diagonal.p, xb, yb, nullptr);
   return CFS_OK;
@@ -229,21 +230,23 @@ int launch_win(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 
 template <typename T>
 int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
-                     void *y_lower_base, cudaStream_t s) {
+                     void *y_lower_base, cudaStream_t s, long long s0,
+                     long long s1) {
   const T *xb = (const T *)x_ext - m->halo_begin;
   T *yb = (T *)y_ext - m->halo_begin;
   T *yl = (T *)y_lower_base;
   const int mode = g_options.diag_mode;
   int variant = g_options.spmv_variant;
-  if (yl && variant != 1)
-    variant = 5; // the fused halo path exists in the register kernels
+  const bool partial = s0 != 0 || s1 != m->nslices;
+  if ((yl || partial) && variant != 1)
+    variant = 5; // halo fusion / slice ranges exist in the register kernels
   // bulk copies of the x / y windows need 16-byte aligned vectors
   // the compressed-index kernel pays off when slices are regular; ragged
   // matrices run the generic warp-per-slice kernel (more registers, no spills)
   if (variant == 5 && m->ccol.p && mode == 0 &&
       m->nregular * 8 >= m->nslices)
-    return launch_reg<T>(m, xb, yb, yl, s);
-  if (variant == 5 || yl)
+    return launch_reg<T>(m, xb, yb, yl, s, s0, s1);
+  if (variant == 5 || yl || partial)
     variant = 1;
   if (variant >= 3 &&
       (!m->sell_slot.p || (((uintptr_t)x_ext | (uintptr_t)y_ext) & 15)))
@@ -268,16 +271,16 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   }
   switch (mode) {
   case 1:
-    launch_sell<T, 1>(m, xb, yb, yl, s);
+    launch_sell<T, 1>(m, xb, yb, yl, s, s0, s1);
     break;
   case 2:
-    launch_sell<T, 2>(m, xb, yb, yl, s);
+    launch_sell<T, 2>(m, xb, yb, yl, s, s0, s1);
     break;
   case 3:
-    launch_sell<T, 3>(m, xb, yb, yl, s);
+    launch_sell<T, 3>(m, xb, yb, yl, s, s0, s1);
     break;
   default:
-    launch_sell<T, 0>(m, xb, yb, yl, s);
+    launch_sell<T, 0>(m, xb, yb, yl, s, s0, s1);
     break;
   }
   return CFS_OK;
@@ -287,18 +290,23 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
 
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1,
-                    void *y_lower_base, bool y_is_zero) {
+                    void *y_lower_base, bool y_is_zero, long long slice0,
+                    long long slice1) {
+  if (slice1 < 0)
+    slice1 = m->nslices;
   const size_t vs = m->vsize();
   const size_t ext_len = (size_t)(m->row_begin + m->nrows - m->halo_begin);
   if (!y_is_zero)
     CFS_CUDA_TRY(cudaMemsetAsync(y_ext, 0, ext_len * vs, s));
-  if (m->nslices == 0)
+  if (m->nslices == 0 || slice1 <= slice0)
     return CFS_OK;
   if (ev0)
     CFS_CUDA_TRY(cudaEventRecord(ev0, s));
   CFS_TRY(m->is_double
-              ? launch_sym_typed<double>(m, y_ext, x_ext, y_lower_base, s)
-              : launch_sym_typed<float>(m, y_ext, x_ext, y_lower_base, s));
+              ? launch_sym_typed<double>(m, y_ext, x_ext, y_lower_base, s,
+                                         slice0, slice1)
+              : launch_sym_typed<float>(m, y_ext, x_ext, y_lower_base, s,
+                                        slice0, slice1));
   CFS_CUDA_TRY(cudaGetLastError());
   if (ev1)
     CFS_CUDA_TRY(cudaEventRecord(ev1, s));

@@ -348,3 +348,44 @@ def test_regular_slices_and_windows_are_found(gpu):
     assert B.info()["regular_slices"] == 0
     A.close()
     B.close()
+
+
+def test_host_vector_pipeline(gpu):
+    """cfs_cuda_spmv with host x / y overlaps H2D, kernel and D2H chunk by
+    chunk on matrices in natural row order; same result as the bulk path"""
+    spec = capi.GenSpec.laplacian(27, 64, 64, 48)
+    rp, ci, v = capi.gen_host_csr(spec)
+    n = spec.nrows
+    x = gen.gen_x(21, n)
+    ref = oracle.Oracle(rp, ci, v, 1).spmv(x)
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(1)
+    assert A.info()["sort_window"] == 0
+    try:
+        ys = {}
+        for pipeline in (1, 0):
+            capi.set_option("pipeline", pipeline)
+            y = np.full(n, 9.0)
+            for _ in range(3):
+                A.spmv(y, x)
+            assert cases.normwise_rel_err(y, ref) <= 1e-12
+            ys[pipeline] = y
+        assert cases.normwise_rel_err(ys[1], ys[0]) <= 1e-13
+    finally:
+        capi.set_option("pipeline", 1)
+        A.close()
+    # banded, single precision: rows reach 700 columns down, chunks overlap
+    spec = capi.GenSpec.banded(200000, 700, 152, 5)
+    rp, ci, v = capi.gen_host_csr(spec, dtype=np.float32)
+    x = gen.gen_x(22, spec.nrows, np.float32)
+    ref = oracle.Oracle(rp, ci, v, 1).spmv(x)
+    capi.set_option("sort_rows", 0)   # keep natural order => pipelined path
+    try:
+        B = capi.Matrix.from_csr(rp, ci, v)
+        B.tune(1)
+        y = np.zeros(spec.nrows, np.float32)
+        B.spmv(y, x)
+        assert cases.normwise_rel_err(y, ref) <= 1e-5
+        B.close()
+    finally:
+        capi.set_option("sort_rows", 1)
