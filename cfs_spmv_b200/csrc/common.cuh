@@ -133,7 +133,6 @@ struct cfs_matrix_s {
   cfsb::DevArray<cfsb::TileRec> tile_rec;
   // variant 3: index stream rewritten to window slots / far codes
   cfsb::DevArray<int32_t> sell_slot;  // padded_entries
-  cfsb::DevArray<char> zeros;         // clears the y accumulator by bulk copy
   int64_t far_entries = 0;            // entries left on the global-RED path
 
   // reference-compatible metadata for P partitions

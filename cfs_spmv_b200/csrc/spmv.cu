@@ -15,9 +15,11 @@
 //     diagonal term is folded into the direct-term accumulator and every
 //     contribution reaches y through an L2 reduction (RED / bulk reduce-add).
 //
-// Variant 1 (this file): non-persistent, direct L1-bypassing loads.
-// Variants 2, 3 (spmv_tma.cuh): persistent, TMA-staged; 3 adds shared-memory
-// x / y windows flushed with bulk reduce-adds.
+// Variant 1 (this file): one warp per slice, direct L1-bypassing loads.
+// Variant 2 (spmv_tma.cuh): persistent, tiles staged in shared memory by TMA.
+// Variant 4 (spmv_win.cuh): x / y windows in shared memory, owner warp per slot.
+// Variant 5 (spmv_reg.cuh, default): compressed index stream for regular
+//   slices, shuffle-merged REDs, optional fused NVLink halo reduction.
 #include "common.cuh"
 #include "spmv_tma.cuh"
 #include "spmv_win.cuh"
@@ -151,9 +153,7 @@ __global__ void __launch_bounds__(kSpmvThreads)
     y[row] = acc;
 }
 
-// ring depth: the windowed kernel has little shared memory left per stage
-// and no global latency in its consumers, so it runs a deeper ring
-constexpr int kStagesPlain = 2, kStagesWindows = 3;
+constexpr int kStages = 2; // ring depth of the persistent kernel
 
 template <typename T, int MODE>
 void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
@@ -170,12 +170,11 @@ void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
         (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr);
 }
 
-template <typename T, bool WINDOWS, int MODE>
+template <typename T, int MODE>
 int launch_tma(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
   static int num_sms = 0, max_ctas = 0;
-  constexpr int kStages = WINDOWS ? kStagesWindows : kStagesPlain;
-  const int smem_bytes = tma::Stage<T, WINDOWS>::smem_bytes(kStages);
-  auto kernel = tma::sym_spmv_tma_kernel<T, kStages, WINDOWS, MODE>;
+  const int smem_bytes = tma::Stage<T>::smem_bytes(kStages);
+  auto kernel = tma::sym_spmv_tma_kernel<T, kStages, MODE>;
   if (!num_sms) {
     int dev = 0;
     CFS_CUDA_TRY(cudaGetDevice(&dev));
@@ -197,8 +196,8 @@ int launch_tma(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
   const int grid = (int)(m->ntiles < want ? m->ntiles : want);
   kernel<<<grid, kTileSlices * 32, smem_bytes, s>>>(
       (int)m->ntiles, m->row_begin, m->tile_rec.p, m->vrow_row.p,
-      WINDOWS ? m->sell_slot.p : m->sell_col.p, (const T *)m->sell_val.p,
-      (const T *)m->diagonal.p, xb, yb);
+      m->sell_col.p, (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb,
+      yb);
   return CFS_OK;
 }
 
@@ -260,13 +259,13 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   if (variant == 2) {
     switch (mode) {
     case 1:
-      return launch_tma<T, false, 1>(m, xb, yb, s);
+      return launch_tma<T, 1>(m, xb, yb, s);
     case 2:
-      return launch_tma<T, false, 2>(m, xb, yb, s);
+      return launch_tma<T, 2>(m, xb, yb, s);
     case 3:
-      return launch_tma<T, false, 3>(m, xb, yb, s);
+      return launch_tma<T, 3>(m, xb, yb, s);
     default:
-      return launch_tma<T, false, 0>(m, xb, yb, s);
+      return launch_tma<T, 0>(m, xb, yb, s);
     }
   }
   switch (mode) {

@@ -44,14 +44,14 @@ __device__ __forceinline__ int ld_stream(const int *p) {
   return v;
 }
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kMaxChain = 3;
 constexpr int kUnroll = 4;
 
 // 8 CTAs of 256 threads per SM: the kernel is latency-bound, occupancy wins over
-// registers (measured: 275 us at 40 registers, 239 us at 32)
+// registers (measured: 275 us at 40 registers, 239 us at 32, 231 us with 128-thread CTAs)
 template <typename T, bool HALO>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, 16)
     sym_spmv_reg_kernel(long long slice_begin, long long slice_end,
                         int row_begin,
                         const int *__restrict__ slice_ptr,

@@ -1,25 +1,17 @@
-// spmv_tma.cuh -- persistent, TMA-staged symmetric SpMV kernels (variants 2, 3).
+// spmv_tma.cuh -- PTX helpers shared by the kernels (TMA bulk copies,
+// mbarriers, L2 reductions) and variant 2, the persistent TMA-staged kernel.
 //
-// A tile is <= kTileSlices consecutive slices (<= kTileSteps slice-steps): its
-// values, indices, row tags and its 128-byte TileRec are contiguous pieces of
-// global memory. Tiles stream through a ring of shared-memory stages with
-// cp.async.bulk (TMA engine, SASS UBLKCP), completion on an mbarrier; the
-// consumer warps, one slice each, read entries from shared memory. Every HBM
+// Variant 2: a tile is <= kTileSlices consecutive slices (<= kTileSteps
+// slice-steps); its values, indices, row tags and its 128-byte TileRec are
+// contiguous pieces of global memory. Tiles stream through a ring of
+// shared-memory stages with cp.async.bulk (TMA engine, SASS UBLKCP), completion
+// on an mbarrier; the consumer warps, one slice each, read entries from shared
+// memory, gather x through L1/L2 and issue the transposed-term REDs. Every HBM
 // request is a large contiguous burst with an L2 evict-first hint, so the
 // streamed matrix does not push x and y out of the 126 MB L2.
-//
-// Variant 2: x gathered through L1/L2, transposed term by global RED.
-// Variant 3 (windows): the columns a tile touches are covered by a few
-//   32-column-aligned windows (windows.cu). The x windows -- and, for tiles of
-//   consecutive rows, x[row] and diagonal[row] -- are bulk-copied next to the
-//   tile, so the consumers never wait on a global load. The transposed term
-//   accumulates into a shared-memory copy of the y windows with plain
-//   read-modify-writes: every slot has ONE owner warp (the GPU restatement of
-//   the reference's conflict-free idea inside a CTA); entries that hit a slot
-//   of another warp go out as global REDs. After the tile the accumulator is
-//   flushed with coalesced REDs, one per slot instead of one per entry, and
-//   left clean. This is the "compressed local vector" of the reference's
-//   methods 2/3 kept in shared memory.
+// Measured (tools/tma_bench.cu): bulk copies issued by ONE warp are serviced one
+// after the other (~0.25 us each whatever their size); copies issued by
+// different warps overlap. Hence lane 0 of every warp issues a share.
 #pragma once
 
 #include "common.cuh"
@@ -60,7 +52,7 @@ __device__ __forceinline__ void load_1d(void *dst, const void *src,
                "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
-// reused data (x): default L2 policy
+// reused data (x windows): default L2 policy
 __device__ __forceinline__ void load_1d_keep(void *dst, const void *src,
                                              uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::"
@@ -74,7 +66,6 @@ __device__ __forceinline__ void red_add(double *p, double v) {
 __device__ __forceinline__ void red_add(float *p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-
 // Remote reduction: the target lives in a peer GPU's memory (NVLink, mapped
 // through symmetric memory), so the reduction is issued at system scope.
 __device__ __forceinline__ void red_add_sys(double *p, double v) {
@@ -98,32 +89,9 @@ __device__ __forceinline__ void y_add(T *y, T *y_lower, int row_begin, int col,
     red_add(y + col, v);
 }
 
-constexpr int kWinSlots = kWindowBlocks * 32;
 constexpr int kTileRows = kTileSlices * kSliceRows;
 
-// Shared-memory stage. WINDOWS adds the x window and the row vectors.
-template <typename T, bool WINDOWS> struct Stage {
-  static constexpr int kVals = kTileSteps * kSliceRows * (int)sizeof(T);
-  static constexpr int kCols = kTileSteps * kSliceRows * 4;
-  static constexpr int kTags = kTileRows * 4;
-  static constexpr int kRec = (int)sizeof(TileRec);
-  static constexpr int kWin = WINDOWS ? kWinSlots * (int)sizeof(T) : 0;
-  static constexpr int kRowVec = WINDOWS ? kTileRows * (int)sizeof(T) : 0;
-  static constexpr int oVals = 0;
-  static constexpr int oCols = oVals + kVals;
-  static constexpr int oTags = oCols + kCols;
-  static constexpr int oRec = oTags + kTags;
-  static constexpr int oXwin = oRec + kRec;
-  static constexpr int oXrow = oXwin + kWin;
-  static constexpr int oDrow = oXrow + kRowVec;
-  static constexpr int kBytes = oDrow + kRowVec;
-  // stages, mbarriers (128 B), two y accumulators (ping-pong)
-  static constexpr int smem_bytes(int stages) {
-    return stages * kBytes + 128 + 2 * kWin;
-  }
-};
-
-// What an issuing lane keeps in registers about a tile.
+// The part of a TileRec an issuing lane keeps in registers.
 struct IssueInfo {
   int4 head;        // slice_begin, nslices, step_begin, nsteps
   int nwin, row_lo;
@@ -156,29 +124,22 @@ __device__ __forceinline__ int win_nblk_of(const IssueInfo &ii, int j) {
   const int v[4] = {ii.nblk.x, ii.nblk.y, ii.nblk.z, ii.nblk.w};
   return (v[j >> 1] >> ((j & 1) * 16)) & 0xffff;
 }
-// global column of window slot `i`
-__device__ __forceinline__ int col_of_slot(const IssueInfo &ii, int i) {
-  int col = 0, off = 0;
-#pragma unroll
-  for (int j = 0; j < kMaxWindows; ++j) {
-    if (j < ii.nwin) {
-      const int n = win_nblk_of(ii, j) * 32;
-      if (i >= off && i < off + n)
-        col = win_lo_of(ii, j) + (i - off);
-      off += n;
-    }
-  }
-  return col;
-}
 
-// Column codes in the index stream:
-//   >= 0 : variant 2: global column; variant 3: owned window slot
-//   -1   : padding
-//   variant 3 only, t = -(code + 2):
-//     t <  kWinSlots : window slot t owned by another warp (x from the window,
-//                      y by global RED)
-//     t >= kWinSlots : column t - kWinSlots outside every window
-template <typename T, int STAGES, bool WINDOWS, int MODE>
+// Shared-memory stage of variant 2.
+template <typename T> struct Stage {
+  static constexpr int kVals = kTileSteps * kSliceRows * (int)sizeof(T);
+  static constexpr int kCols = kTileSteps * kSliceRows * 4;
+  static constexpr int kTags = kTileRows * 4;
+  static constexpr int oVals = 0;
+  static constexpr int oCols = oVals + kVals;
+  static constexpr int oTags = oCols + kCols;
+  static constexpr int oRec = oTags + kTags;
+  static constexpr int kBytes = oRec + (int)sizeof(TileRec);
+  static constexpr int smem_bytes(int stages) { return stages * kBytes + 128; }
+};
+
+// MODE: measurement aid, see spmv.cu (non-zero modes compute wrong results).
+template <typename T, int STAGES, int MODE>
 __global__ void __launch_bounds__(kTileRows)
     sym_spmv_tma_kernel(int ntiles, int row_begin,
                         const TileRec *__restrict__ tile_rec,
@@ -187,10 +148,9 @@ __global__ void __launch_bounds__(kTileRows)
                         const T *__restrict__ sell_val,
                         const T *__restrict__ diagonal,
                         const T *__restrict__ x, T *__restrict__ y) {
-  typedef Stage<T, WINDOWS> L;
+  typedef Stage<T> L;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * L::kBytes);
-  T *const yacc = reinterpret_cast<T *>(smem + STAGES * L::kBytes + 128);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int stride = gridDim.x;
 
@@ -202,72 +162,34 @@ __global__ void __launch_bounds__(kTileRows)
       mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (WINDOWS) {
-    // accumulators start clean; every flush leaves them clean again
-    for (int i = tid; i < 2 * kWinSlots; i += kTileRows)
-      yacc[i] = T(0);
-  }
   __syncthreads();
 
-  // All loads of one tile. Bulk copies issued by one warp are serviced one
-  // after the other (~0.25 us each, measured with tools/tma_bench.cu), copies
-  // issued by different warps overlap: lane 0 of every warp issues its share
-  // (op o goes to warp o % kTileSlices). Warp 0 also arms the barrier.
-  auto issue = [&](int tile, int stage, const IssueInfo &ii) {
+  // the four copies of a tile, one per warp; warp 0 also arms the barrier
+  auto issue = [&](int tile, int stage, const int4 head) {
     unsigned char *base = smem + stage * L::kBytes;
-    const uint32_t nent = (uint32_t)ii.head.w * kSliceRows;
+    const uint32_t nent = (uint32_t)head.w * kSliceRows;
     const uint32_t vb = nent * (uint32_t)sizeof(T), cb = nent * 4u,
-                   tb = (uint32_t)ii.head.y * kSliceRows * 4u;
-    const uint32_t rb =
-        ii.row_lo >= 0 ? (uint32_t)ii.head.y * kSliceRows * (uint32_t)sizeof(T)
-                       : 0u;
-    if (warp == 0) {
-      uint32_t total = vb + cb + tb + (uint32_t)sizeof(TileRec) + 2u * rb;
-      if (WINDOWS) {
-#pragma unroll
-        for (int j = 0; j < kMaxWindows; ++j)
-          if (j < ii.nwin)
-            total += (uint32_t)win_nblk_of(ii, j) * 32u * (uint32_t)sizeof(T);
-      }
-      mbar_expect_tx(&full[stage], total);
-    }
-    const size_t e0 = (size_t)ii.head.z * kSliceRows;
+                   tb = (uint32_t)head.y * kSliceRows * 4u;
+    if (warp == 0)
+      mbar_expect_tx(&full[stage], vb + cb + tb + (uint32_t)sizeof(TileRec));
+    const size_t e0 = (size_t)head.z * kSliceRows;
     if (warp == 0 % kTileSlices && nent)
       load_1d(base + L::oVals, sell_val + e0, vb, &full[stage], policy);
     if (warp == 1 % kTileSlices && nent)
       load_1d(base + L::oCols, sell_col + e0, cb, &full[stage], policy);
     if (warp == 2 % kTileSlices)
-      load_1d(base + L::oTags, vrow_row + (size_t)ii.head.x * kSliceRows, tb,
+      load_1d(base + L::oTags, vrow_row + (size_t)head.x * kSliceRows, tb,
               &full[stage], policy);
     if (warp == 3 % kTileSlices)
       load_1d(base + L::oRec, &tile_rec[tile], (uint32_t)sizeof(TileRec),
               &full[stage], policy);
-    if (WINDOWS) {
-      if (rb && warp == 2 % kTileSlices)
-        load_1d_keep(base + L::oXrow, x + ii.row_lo, rb, &full[stage]);
-      if (rb && warp == 3 % kTileSlices)
-        load_1d(base + L::oDrow, diagonal + (ii.row_lo - row_begin), rb,
-                &full[stage], policy);
-      T *xw = reinterpret_cast<T *>(base + L::oXwin);
-      int off = 0;
-#pragma unroll
-      for (int j = 0; j < kMaxWindows; ++j) {
-        if (j < ii.nwin) {
-          const int n = win_nblk_of(ii, j) * 32;
-          if (warp == j % kTileSlices)
-            load_1d_keep(xw + off, x + win_lo_of(ii, j),
-                         (uint32_t)n * sizeof(T), &full[stage]);
-          off += n;
-        }
-      }
-    }
   };
 
   if (lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       const int t = blockIdx.x + s * stride;
       if (t < ntiles)
-        issue(t, s, fetch_issue_info<WINDOWS>(&tile_rec[t]));
+        issue(t, s, *reinterpret_cast<const int4 *>(&tile_rec[t]));
     }
   }
 
@@ -275,112 +197,59 @@ __global__ void __launch_bounds__(kTileRows)
   for (int tile = blockIdx.x; tile < ntiles; tile += stride, ++it) {
     const int stage = it % STAGES;
     const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-    // issuing lanes prefetch what they need for the tile after the ring
+    // issuing lanes prefetch the header of the tile they will issue next
     const int t_next = tile + STAGES * stride;
-    IssueInfo next;
+    int4 head_next = make_int4(0, 0, 0, 0);
     if (lane == 0 && t_next < ntiles)
-      next = fetch_issue_info<WINDOWS>(&tile_rec[t_next]);
+      head_next = *reinterpret_cast<const int4 *>(&tile_rec[t_next]);
 
     unsigned char *base = smem + stage * L::kBytes;
     mbar_wait(&full[stage], parity);
     const TileRec *rec = reinterpret_cast<const TileRec *>(base + L::oRec);
-    T *yw = yacc + (it & 1) * kWinSlots;
-    IssueInfo mine; // window table of this tile (the stage is recycled early)
-    if (WINDOWS)
-      mine = fetch_issue_info<true>(rec);
     if (warp < rec->nslices) {
       const T *vals = reinterpret_cast<const T *>(base + L::oVals);
       const int *cols = reinterpret_cast<const int *>(base + L::oCols);
       const int *tags = reinterpret_cast<const int *>(base + L::oTags);
-      const T *xw = reinterpret_cast<const T *>(base + L::oXwin);
       const int tag = tags[warp * kSliceRows + lane];
       const bool active = tag >= 0;
       const int row = tag & kVrowRowMask;
       T xr = 0, acc = 0;
-      if (WINDOWS && mine.row_lo >= 0) {
-        // consecutive rows: x[row] and diagonal[row] came with the tile
-        xr = reinterpret_cast<const T *>(base + L::oXrow)[tid];
-        acc = reinterpret_cast<const T *>(base + L::oDrow)[tid] * xr;
-      } else if (active) {
+      if (active) {
         xr = x[row];
         if (!(tag & kVrowCont))
           acc = diagonal[row - row_begin] * xr;
       }
       int k = rec->slice_step[warp] * kSliceRows + lane;
       const int kend = rec->slice_step[warp + 1] * kSliceRows + lane;
-      if (!WINDOWS) {
-        constexpr int U = 8;
-        for (; k + (U - 1) * kSliceRows < kend; k += U * kSliceRows) {
-          int c[U];
-          T xc[U];
+      constexpr int U = 8;
+      for (; k + (U - 1) * kSliceRows < kend; k += U * kSliceRows) {
+        int c[U];
+        T xc[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            c[u] = cols[k + u * kSliceRows];
+        for (int u = 0; u < U; ++u)
+          c[u] = cols[k + u * kSliceRows];
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            xc[u] = c[u] >= 0 ? ((MODE & 2) ? xr : x[c[u]]) : T(0);
+        for (int u = 0; u < U; ++u)
+          xc[u] = c[u] >= 0 ? ((MODE & 2) ? xr : x[c[u]]) : T(0);
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (c[u] >= 0) {
-              const T a = vals[k + u * kSliceRows];
-              acc += a * xc[u];
-              if (!(MODE & 1))
-                red_add(y + c[u], a * xr);
-              else
-                acc += a * xr;
-            }
-          }
-        }
-        for (; k < kend; k += kSliceRows) {
-          const int c = cols[k];
-          if (c >= 0) {
-            const T a = vals[k];
-            acc += a * ((MODE & 2) ? xr : x[c]);
+        for (int u = 0; u < U; ++u) {
+          if (c[u] >= 0) {
+            const T a = vals[k + u * kSliceRows];
+            acc += a * xc[u];
             if (!(MODE & 1))
-              red_add(y + c, a * xr);
+              red_add(y + c[u], a * xr);
+            else
+              acc += a * xr;
           }
         }
-      } else {
-        // pass 1: owned slots -- shared memory only. A plain read-modify-write
-        // is enough (one owner warp per slot); __syncwarp orders the steps.
-        unsigned far_lo = 0, far_hi = 0; // bit u: my entry of step u is far
-        const int kbeg = k;
-        for (int u = 0; k < kend; k += kSliceRows, ++u) {
-          const int c = cols[k];
-          if (c >= 0) {
-            const T a = vals[k];
-            acc += a * xw[c];
-            yw[c] += a * xr;
-          }
-          if (u < 32)
-            far_lo |= (unsigned)(c < -1) << u;
-          else
-            far_hi |= (unsigned)(c < -1) << (u - 32);
-          __syncwarp();
-        }
-        // pass 2: the few far entries. Slots of another warp read x from the
-        // window and only send a RED; columns outside the windows also gather
-        // x from L2. Only steps where some lane holds a far entry are visited.
-        unsigned long long steps =
-            ((unsigned long long)__reduce_or_sync(0xffffffffu, far_hi) << 32) |
-            __reduce_or_sync(0xffffffffu, far_lo);
-        while (steps) {
-          const int kk = kbeg + (__ffsll((long long)steps) - 1) * kSliceRows;
-          steps &= steps - 1;
-          const int c = cols[kk];
-          if (c < -1) {
-            const int t = -(c + 2);
-            const T a = vals[kk];
-            int gc;
-            if (t < kWinSlots) {
-              acc += a * xw[t];
-              gc = col_of_slot(mine, t);
-            } else {
-              gc = t - kWinSlots;
-              acc += a * x[gc];
-            }
-            red_add(y + gc, a * xr);
-          }
+      }
+      for (; k < kend; k += kSliceRows) {
+        const int c = cols[k];
+        if (c >= 0) {
+          const T a = vals[k];
+          acc += a * ((MODE & 2) ? xr : x[c]);
+          if (!(MODE & 1))
+            red_add(y + c, a * xr);
         }
       }
       if (active)
@@ -388,27 +257,7 @@ __global__ void __launch_bounds__(kTileRows)
     }
     __syncthreads(); // every consumer is done with this stage
     if (lane == 0 && t_next < ntiles)
-      issue(t_next, stage, next);
-    if (WINDOWS) {
-      // flush the y windows: every thread reads, clears and RED-adds its
-      // slots. Consecutive threads hold consecutive columns, so a warp-wide
-      // RED is one or two full 128-byte lines. This accumulator is used again
-      // two tiles later, i.e. behind the next tile's barrier.
-      int off = 0;
-#pragma unroll
-      for (int j = 0; j < kMaxWindows; ++j) {
-        if (j < mine.nwin) {
-          const int n = win_nblk_of(mine, j) * 32;
-          T *dst = y + win_lo_of(mine, j);
-          for (int i = tid; i < n; i += kTileRows) {
-            const T v = yw[off + i];
-            yw[off + i] = T(0);
-            red_add(dst + i, v);
-          }
-          off += n;
-        }
-      }
-    }
+      issue(t_next, stage, head_next);
   }
 }
 

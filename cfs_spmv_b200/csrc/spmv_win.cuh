@@ -53,7 +53,7 @@ __device__ __forceinline__ int ld_stream(const int *p) {
 }
 
 constexpr int kWinSlots = kWindowBlocks * 32;
-constexpr int kTileRows = kTileSlices * kSliceRows;
+using tma::kTileRows;
 constexpr int kBatch = 7; // entries per lane in flight
 
 template <typename T>

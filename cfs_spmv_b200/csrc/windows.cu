@@ -223,8 +223,6 @@ int build_windows(cfs_matrix_s *m, cudaStream_t s) {
   const int vec_end = m->row_begin + m->nrows;
   const int col_limit = vec_end & ~31;
   CFS_TRY(m->sell_slot.alloc((size_t)m->padded_entries));
-  CFS_TRY(m->zeros.alloc((size_t)kWindowBlocks * 32 * 8));
-  CFS_CUDA_TRY(cudaMemsetAsync(m->zeros.p, 0, (size_t)kWindowBlocks * 32 * 8, s));
   DevArray<unsigned long long> far;
   CFS_TRY(far.alloc(1));
   CFS_CUDA_TRY(cudaMemsetAsync(far.p, 0, 8, s));

@@ -52,8 +52,9 @@ int cfs_cuda_init(int device);
 const char *cfs_cuda_last_error(void);
 const char *cfs_cuda_version(void);
 /* run-time tunables (the CFS_GPU_* knobs): "spmv_variant" 1 = one warp per
- * slice with direct loads, 2 = persistent TMA-staged kernel, 3 = TMA-staged
- * with shared-memory x/y windows and bulk reduce-add flush;
+ * slice with direct loads, 2 = persistent TMA-staged kernel, 4 = shared-memory
+ * x/y windows, 5 = compressed index stream + shuffle-merged REDs (default);
+ * "sort_rows", "pipeline" 0/1;
  * "ctas_per_sm" for the persistent kernel. Returns CFS_ERR_INVALID for an
  * unknown key. */
 int cfs_cuda_set_option(const char *key, long long value);
