@@ -24,7 +24,7 @@ OBJDIR = os.path.join(ROOT, "build", "obj")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-CUDA_SOURCES = ["cfs_cuda.cu", "preproc.cu", "windows.cu", "compress.cu",
+CUDA_SOURCES = ["cfs_cuda.cu", "preproc.cu", "windows.cu", "compress.cu", "hubs.cu",
                 "refmeta.cu",
                 "spmv.cu", "gen.cu"]
 NVCC_FLAGS = [

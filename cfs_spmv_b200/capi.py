@@ -88,6 +88,8 @@ class MatrixInfo(ctypes.Structure):
                 ("ntiles", ctypes.c_int64), ("far_entries", ctypes.c_int64),
                 ("regular_slices", ctypes.c_int64),
                 ("index_rows", ctypes.c_int64),
+                ("hub_columns", ctypes.c_int64),
+                ("hub_entries", ctypes.c_int64),
                 ("sort_window", ctypes.c_int64)]
 
     def as_dict(self):

@@ -98,6 +98,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.sort_rows = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "hubs") && (value == 0 || value == 1)) {
+    g_options.hubs = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "pipeline") && (value == 0 || value == 1)) {
     g_options.pipeline = (int)value;
     return CFS_OK;
@@ -341,6 +345,7 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
     CFS_TRY(build_layout(m, m->stream));
     CFS_TRY(build_windows(m, m->stream));
     CFS_TRY(build_compressed_cols(m, m->stream));
+    CFS_TRY(build_hubs(m, m->stream));
     CFS_TRY(build_pipeline_plan(m, m->stream));
     // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
     m->row_split.assign((size_t)nparts + 1, 0);
@@ -420,6 +425,8 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
   info->ntiles = m->ntiles;
   info->far_entries = m->far_entries;
   info->regular_slices = m->nregular;
+  info->hub_columns = m->nhubs;
+  info->hub_entries = m->hub_entries;
   info->sort_window = m->sort_window;
   info->index_rows = m->ccol_rows;
   if (m->symmetric && m->tuned) {
@@ -445,7 +452,9 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
                 m->low_colind.bytes() + m->low_values.bytes() +
                 m->diagonal.bytes() + m->slice_ptr.bytes() +
                 m->vrow_row.bytes() + m->sell_col.bytes() +
-                m->sell_val.bytes() + m->tile_rec.bytes() + m->sell_slot.bytes() + m->ccol.bytes() + m->slice_cptr.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
+                m->sell_val.bytes() + m->tile_rec.bytes() + m->hub_ptr.bytes() + m->hub_row.bytes() +
+                m->hub_val.bytes() + m->hub_colstream.bytes() +
+                m->hub_chunks.bytes() + m->sell_slot.bytes() + m->ccol.bytes() + m->slice_cptr.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
                 m->adj.bytes() + m->color.bytes() + m->color_first.bytes() +
                 m->range_ptr.bytes() + m->part_nranges.bytes() +
                 m->range_start.bytes() + m->range_end.bytes() +

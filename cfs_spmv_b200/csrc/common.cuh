@@ -39,6 +39,11 @@ constexpr int kMaxChunk = 32;        // longest virtual row; longer rows are spl
 constexpr int kVrowCont = 1 << 30;   // flag: virtual row continues an earlier chunk
 constexpr int kVrowRowMask = kVrowCont - 1;
 constexpr int kSliceRegular = 1 << 30; // flag in slice_cptr: regular slice
+// hub columns (hubs.cu)
+constexpr int kHubMinCount = 128; // lower entries that make a column a hub
+constexpr int kHubChunk = 1024;   // entries of a hub column per warp
+constexpr int kHubFlag = 1 << 30; // in the row stream: transposed term is done
+                                  // column-wise, skip the RED
 // Persistent TMA-staged kernel: a tile is up to kTileSlices consecutive slices
 // whose entries (<= kTileSteps slice-steps of 32) are one contiguous piece of
 // the value / index streams, fetched by one bulk copy each.
@@ -64,6 +69,7 @@ static_assert(sizeof(TileRec) == 128, "TileRec must stay 128 bytes");
 struct Options {
   int spmv_variant = 5;
   int ctas_per_sm = 2;
+  int hubs = 1;      // column-wise handling of hub columns of ragged matrices
   int pipeline = 1;  // overlap H2D / kernel / D2H in cfs_cuda_spmv(host, host)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
@@ -129,6 +135,11 @@ struct cfs_matrix_s {
   cfsb::DevArray<int32_t> slice_cptr; // nslices+1; bit 30 = regular
   cfsb::DevArray<int32_t> ccol;
   int64_t nregular = 0, ccol_rows = 0;
+  // hub columns of ragged matrices (hubs.cu)
+  int64_t nhubs = 0, hub_entries = 0, nhub_chunks = 0;
+  cfsb::DevArray<int32_t> hub_ptr, hub_row, hub_colstream;
+  cfsb::DevArray<char> hub_val;
+  cfsb::DevArray<int4> hub_chunks;    // {column, first entry, end entry, -}
   int64_t ntiles = 0;
   cfsb::DevArray<cfsb::TileRec> tile_rec;
   // variant 3: index stream rewritten to window slots / far codes
@@ -169,6 +180,10 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s);
 int build_windows(cfs_matrix_s *m, cudaStream_t s);
 // index-stream compression of regular slices (compress.cu)
 int build_compressed_cols(cfs_matrix_s *m, cudaStream_t s);
+// hub columns (hubs.cu)
+int build_hubs(cfs_matrix_s *m, cudaStream_t s);
+int launch_hub_spmv(const cfs_matrix_s *m, void *y, const void *x,
+                    cudaStream_t s);
 // reference metadata (refmeta.cu)
 int build_refmeta(cfs_matrix_s *m, cudaStream_t s);
 // kernels (spmv.cu)

@@ -61,7 +61,7 @@ constexpr int kUnroll = 4;
 //
 // x and y are "virtual base" pointers: indexed by GLOBAL row/column id (for a
 // shard they point halo_begin elements before the extended local vector).
-template <typename T, int MODE, bool HALO>
+template <typename T, int MODE, bool HALO, bool HUBS>
 __global__ void __launch_bounds__(kSpmvThreads)
     sym_spmv_sell_kernel(long long slice_begin, long long slice_end,
                          int row_begin,
@@ -99,28 +99,38 @@ __global__ void __launch_bounds__(kSpmvThreads)
       a[u] = ld_stream(vp + u * kSliceRows);
     }
     T xc[kUnroll];
+    bool hub[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    for (int u = 0; u < kUnroll; ++u) {
+      // hub columns: the transposed term is done column-wise by
+      // hub_spmv_kernel (hubs.cu); only the direct term stays here
+      hub[u] = HUBS && c[u] >= 0 && (c[u] & kHubFlag);
+      if (HUBS && c[u] >= 0)
+        c[u] &= ~kHubFlag;
       xc[u] = c[u] >= 0 ? ((MODE & 2) ? xr : x[c[u]]) : T(0);
+    }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (c[u] >= 0) {
         acc += a[u] * xc[u];
-        if (!(MODE & 1))
-          tma::y_add<HALO>(y, y_lower, row_begin, c[u], a[u] * xr);
-        else
+        if (MODE & 1)
           acc += a[u] * xr;
+        else if (!hub[u])
+          tma::y_add<HALO>(y, y_lower, row_begin, c[u], a[u] * xr);
       }
     }
     cp += kUnroll * kSliceRows;
     vp += kUnroll * kSliceRows;
   }
   for (; w > 0; --w) {
-    const int c = ld_stream(cp);
+    int c = ld_stream(cp);
     const T a = ld_stream(vp);
     if (c >= 0) {
+      const bool hub = HUBS && (c & kHubFlag);
+      if (HUBS)
+        c &= ~kHubFlag;
       acc += a * ((MODE & 2) ? xr : x[c]);
-      if (!(MODE & 1))
+      if (!(MODE & 1) && !hub)
         tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
     }
     cp += kSliceRows;
@@ -160,14 +170,24 @@ void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
                  cudaStream_t s, long long s0, long long s1) {
   const unsigned grid =
       (unsigned)(((s1 - s0) * 32 + kSpmvThreads - 1) / kSpmvThreads);
+  // hub columns: flagged column stream + a second, column-wise kernel
+  const bool hubs = MODE == 0 && !y_lower && m->nhubs > 0 && g_options.hubs &&
+                    s0 == 0 && s1 == m->nslices;
   if (y_lower)
-    sym_spmv_sell_kernel<T, MODE, true><<<grid, kSpmvThreads, 0, s>>>(
+    sym_spmv_sell_kernel<T, MODE, true, false><<<grid, kSpmvThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
         (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower);
+  else if (hubs)
+    sym_spmv_sell_kernel<T, MODE, false, true><<<grid, kSpmvThreads, 0, s>>>(
+        s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p,
+        m->hub_colstream.p, (const T *)m->sell_val.p,
+        (const T *)m->diagonal.p, xb, yb, nullptr);
   else
-    sym_spmv_sell_kernel<T, MODE, false><<<grid, kSpmvThreads, 0, s>>>(
+    sym_spmv_sell_kernel<T, MODE, false, false><<<grid, kSpmvThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
         (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr);
+  if (hubs)
+    launch_hub_spmv(m, yb, xb, s);
 }
 
 template <typename T, int MODE>

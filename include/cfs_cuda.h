@@ -54,7 +54,7 @@ const char *cfs_cuda_version(void);
 /* run-time tunables (the CFS_GPU_* knobs): "spmv_variant" 1 = one warp per
  * slice with direct loads, 2 = persistent TMA-staged kernel, 4 = shared-memory
  * x/y windows, 5 = compressed index stream + shuffle-merged REDs (default);
- * "sort_rows", "pipeline" 0/1;
+ * "sort_rows", "pipeline", "hubs" 0/1;
  * "ctas_per_sm" for the persistent kernel. Returns CFS_ERR_INVALID for an
  * unknown key. */
 int cfs_cuda_set_option(const char *key, long long value);
@@ -116,6 +116,8 @@ typedef struct cfs_matrix_info {
   int64_t far_entries; /* entries outside the shared-memory windows (variant 3) */
   int64_t regular_slices; /* slices whose column stream is compressed to bases */
   int64_t index_rows;     /* 128-byte rows of the compressed column stream    */
+  int64_t hub_columns;    /* columns whose transposed term runs column-wise   */
+  int64_t hub_entries;    /* lower entries in those columns                   */
   int64_t sort_window;    /* 0 = natural row order; else rows were sorted by
                              length inside windows of this many rows          */
 } cfs_matrix_info;

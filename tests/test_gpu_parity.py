@@ -389,3 +389,48 @@ def test_host_vector_pipeline(gpu):
         B.close()
     finally:
         capi.set_option("sort_rows", 1)
+
+
+def test_hub_columns_run_column_wise(gpu):
+    """power-law style input: a few columns hold most of the lower triangle.
+    Their transposed term runs column-wise (hubs.cu); result unchanged."""
+    rng = np.random.default_rng(3)
+    n = 6000
+    hubs = [0, 1, 5, 17]
+    pairs = set()
+    for h in hubs:                       # dense columns below the diagonal
+        for i in rng.choice(np.arange(h + 1, n), size=n // 2, replace=False):
+            pairs.add((int(i), h))
+    for _ in range(4 * n):               # sparse background
+        i, j = int(rng.integers(1, n)), int(rng.integers(0, n))
+        if j < i:
+            pairs.add((i, j))
+    hi = np.array([p[0] for p in pairs])
+    lo = np.array([p[1] for p in pairs])
+    val = rng.uniform(-1, 1, size=len(hi))
+    rows = np.concatenate([hi, lo, np.arange(n)])
+    cols = np.concatenate([lo, hi, np.arange(n)])
+    vals = np.concatenate([val, val, np.full(n, 40.0)])
+    order = np.lexsort((cols, rows))
+    rp = np.zeros(n + 1, np.int64)
+    np.add.at(rp, rows + 1, 1)
+    rp = np.cumsum(rp).astype(np.int32)
+    ci, v = cols[order].astype(np.int32), vals[order]
+    x = gen.gen_x(9, n)
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        ref = oracle.Oracle(rp, ci, v.astype(dt), 1).spmv(x.astype(dt))
+        A = capi.Matrix.from_csr(rp, ci, v.astype(dt))
+        A.tune(1)
+        inf = A.info()
+        assert inf["hub_columns"] == len(hubs)
+        assert inf["hub_entries"] >= len(hubs) * (n // 2)
+        try:
+            for use_hubs in (1, 0):
+                capi.set_option("hubs", use_hubs)
+                y = np.full(n, 5.0, dt)
+                for _ in range(2):
+                    A.spmv(y, x.astype(dt))
+                    assert cases.normwise_rel_err(y, ref) <= tol
+        finally:
+            capi.set_option("hubs", 1)
+            A.close()

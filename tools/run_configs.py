@@ -28,7 +28,8 @@ def time_matrix(name, n, rp, ci, v, is_double, iters=50):
            "padded_entries": inf["padded_entries"],
            "padding": inf["padded_entries"] / max(inf["nnz_low"], 1),
            "regular_slices": inf["regular_slices"],
-           "sort_window": inf["sort_window"], "nslices": inf["nslices"],
+           "sort_window": inf["sort_window"], "hub_columns": inf["hub_columns"],
+           "hub_entries": inf["hub_entries"], "nslices": inf["nslices"],
            "tune_s": round(tune_s, 3)}
     for variant in (1, 5):
         capi.set_option("spmv_variant", variant)
