@@ -42,9 +42,11 @@ static int require_device() {
 
 enum PtrKind { kPtrHost, kPtrDevice };
 
-static int classify(const void *p, PtrKind *kind) {
+static int classify(const void *p, PtrKind *kind, bool *pinned = nullptr) {
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (pinned)
+    *pinned = false;
   if (e != cudaSuccess) {
     cudaGetLastError();
     *kind = kPtrHost;
@@ -53,6 +55,8 @@ static int classify(const void *p, PtrKind *kind) {
   *kind = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)
               ? kPtrDevice
               : kPtrHost;
+  if (pinned)
+    *pinned = a.type == cudaMemoryTypeHost;
   return CFS_OK;
 }
 
@@ -104,6 +108,30 @@ int cfs_cuda_set_option(const char *key, long long value) {
   }
   if (!strcmp(key, "pipeline") && (value == 0 || value == 1)) {
     g_options.pipeline = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "pipeline_ramp") && (value == 0 || value == 1)) {
+    g_options.pipeline_ramp = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "pipeline_smem") && value >= 0 && value <= 200 * 1024) {
+    g_options.pipeline_smem = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "pipeline_skip") && value >= 0 && value <= 7) {
+    g_options.pipeline_skip = (int)value; // measurement aid: wrong results
+    return CFS_OK;
+  }
+  if (!strcmp(key, "pipeline_trace") && (value == 0 || value == 1)) {
+    g_options.pipeline_trace = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "pipeline_graph") && (value == 0 || value == 1)) {
+    g_options.pipeline_graph = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "pipeline_chunks") && value >= 2 && value <= 256) {
+    g_options.pipeline_chunks = (int)value;
     return CFS_OK;
   }
   if (!strcmp(key, "diag_mode") && value >= 0 && value <= 3) {
@@ -390,6 +418,14 @@ void cfs_cuda_matrix_destroy(cfs_mat_t m) {
     cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_k)
     cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_d)
+    cudaEventDestroy(e);
+  if (m->ev_fork)
+    cudaEventDestroy(m->ev_fork);
+  if (m->ev_join)
+    cudaEventDestroy(m->ev_join);
+  if (m->pipe_graph)
+    cudaGraphExecDestroy(m->pipe_graph);
   if (m->h2d_stream)
     cudaStreamDestroy(m->h2d_stream);
   if (m->d2h_stream)
@@ -490,7 +526,58 @@ int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
 
 // Host vectors in, host vectors out: H2D of x, the kernel and D2H of y overlap
 // chunk by chunk (see cfs_matrix_s::Chunk). Three streams, events between them.
-static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x) {
+// enqueue_pipeline issues one whole step; with pinned vectors the step is
+// captured ONCE per (x, y) pair into a CUDA graph (about 110 runtime calls
+// become one launch -- the bench loop of the reference, bench_spmv_mmf.cpp:
+// 162-167, calls with the same two vectors every time).
+static int enqueue_pipeline(cfs_mat_t m, void *y, const void *x, bool fork) {
+  const size_t vs = m->vsize();
+  const size_t K = m->chunks.size();
+  char *xd = m->stage_x.p, *yd = m->stage_y.p;
+  if (fork) { // bring the copy streams into the capture
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_fork, m->stream));
+    CFS_CUDA_TRY(cudaStreamWaitEvent(m->h2d_stream, m->ev_fork, 0));
+  }
+  if (g_options.pipeline_trace && !fork)
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_fork, m->stream));
+  CFS_CUDA_TRY(cudaMemsetAsync(yd, 0, (size_t)m->nrows * vs, m->stream));
+  size_t next_out = 0;
+  for (size_t c = 0; c < K; ++c) {
+    const cfs_matrix_s::Chunk &ch = m->chunks[c];
+    const size_t xo = (size_t)ch.row0 * vs;
+    // the last chunk also carries the columns beyond the last row (none for a
+    // square matrix, kept for safety)
+    const size_t xe = (c + 1 == K ? (size_t)m->ncols : (size_t)ch.row1) * vs;
+    if (xe > xo && !(g_options.pipeline_skip & 4))
+      CFS_CUDA_TRY(cudaMemcpyAsync(xd + xo, (const char *)x + xo, xe - xo,
+                                   cudaMemcpyHostToDevice, m->h2d_stream));
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_x[c], m->h2d_stream));
+    CFS_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_x[c], 0));
+    if (!(g_options.pipeline_skip & 1))
+      CFS_TRY(launch_sym_spmv(m, yd, xd, m->stream, nullptr, nullptr, nullptr,
+                              true, ch.slice0, ch.slice1));
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_k[c], m->stream));
+    while (next_out < K && m->chunks[next_out].final_after <= (int)c) {
+      const cfs_matrix_s::Chunk &o = m->chunks[next_out];
+      const size_t yo = (size_t)o.row0 * vs, ye = (size_t)o.row1 * vs;
+      CFS_CUDA_TRY(cudaStreamWaitEvent(m->d2h_stream, m->ev_k[c], 0));
+      if (ye > yo && !(g_options.pipeline_skip & 2))
+        CFS_CUDA_TRY(cudaMemcpyAsync((char *)y + yo, yd + yo, ye - yo,
+                                     cudaMemcpyDeviceToHost, m->d2h_stream));
+      if (g_options.pipeline_trace && !fork)
+        CFS_CUDA_TRY(cudaEventRecord(m->ev_d[next_out], m->d2h_stream));
+      ++next_out;
+    }
+  }
+  if (fork) { // join: the capture ends on m->stream
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_join, m->d2h_stream));
+    CFS_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+  }
+  return CFS_OK;
+}
+
+static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x,
+                               bool pinned) {
   const size_t vs = m->vsize();
   const size_t K = m->chunks.size();
   if (!m->h2d_stream) {
@@ -500,46 +587,63 @@ static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x) {
                                            cudaStreamNonBlocking));
     m->ev_x.resize(K);
     m->ev_k.resize(K);
+    m->ev_d.resize(K);
+    const unsigned flags =
+        g_options.pipeline_trace ? cudaEventDefault : cudaEventDisableTiming;
     for (size_t c = 0; c < K; ++c) {
-      CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_x[c],
-                                            cudaEventDisableTiming));
-      CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_k[c],
-                                            cudaEventDisableTiming));
+      CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_x[c], flags));
+      CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_k[c], flags));
+      CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_d[c], flags));
     }
+    CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_fork, flags));
+    CFS_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   }
   if (!m->stage_x.p)
     CFS_TRY(m->stage_x.alloc((size_t)m->ncols * vs));
   if (!m->stage_y.p)
     CFS_TRY(m->stage_y.alloc((size_t)m->nrows * vs));
-  char *xd = m->stage_x.p, *yd = m->stage_y.p;
-  CFS_CUDA_TRY(cudaMemsetAsync(yd, 0, (size_t)m->nrows * vs, m->stream));
-  size_t next_out = 0;
-  for (size_t c = 0; c < K; ++c) {
-    const cfs_matrix_s::Chunk &ch = m->chunks[c];
-    const size_t xo = (size_t)ch.row0 * vs;
-    // the last chunk also carries the columns beyond the last row (none for a
-    // square matrix, kept for safety)
-    const size_t xe = (c + 1 == K ? (size_t)m->ncols : (size_t)ch.row1) * vs;
-    if (xe > xo)
-      CFS_CUDA_TRY(cudaMemcpyAsync(xd + xo, (const char *)x + xo, xe - xo,
-                                   cudaMemcpyHostToDevice, m->h2d_stream));
-    CFS_CUDA_TRY(cudaEventRecord(m->ev_x[c], m->h2d_stream));
-    CFS_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_x[c], 0));
-    CFS_TRY(launch_sym_spmv(m, yd, xd, m->stream, nullptr, nullptr, nullptr,
-                            true, ch.slice0, ch.slice1));
-    CFS_CUDA_TRY(cudaEventRecord(m->ev_k[c], m->stream));
-    while (next_out < K && m->chunks[next_out].final_after <= (int)c) {
-      const cfs_matrix_s::Chunk &o = m->chunks[next_out];
-      const size_t yo = (size_t)o.row0 * vs, ye = (size_t)o.row1 * vs;
-      CFS_CUDA_TRY(cudaStreamWaitEvent(m->d2h_stream, m->ev_k[c], 0));
-      if (ye > yo)
-        CFS_CUDA_TRY(cudaMemcpyAsync((char *)y + yo, yd + yo, ye - yo,
-                                     cudaMemcpyDeviceToHost, m->d2h_stream));
-      ++next_out;
+  if (pinned && g_options.pipeline_graph) {
+    if (!m->pipe_graph || m->pipe_x != x || m->pipe_y != y) {
+      if (m->pipe_graph) {
+        cudaGraphExecDestroy(m->pipe_graph);
+        m->pipe_graph = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      CFS_CUDA_TRY(cudaStreamBeginCapture(m->stream,
+                                          cudaStreamCaptureModeThreadLocal));
+      const int status = enqueue_pipeline(m, y, x, true);
+      const cudaError_t e = cudaStreamEndCapture(m->stream, &graph);
+      if (status != CFS_OK) {
+        if (graph)
+          cudaGraphDestroy(graph);
+        return status;
+      }
+      CFS_CUDA_TRY(e);
+      const cudaError_t ei = cudaGraphInstantiate(&m->pipe_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      CFS_CUDA_TRY(ei);
+      m->pipe_x = x;
+      m->pipe_y = y;
     }
+    CFS_CUDA_TRY(cudaGraphLaunch(m->pipe_graph, m->stream));
+    CFS_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return CFS_OK;
   }
+  CFS_TRY(enqueue_pipeline(m, y, x, false));
   CFS_CUDA_TRY(cudaStreamSynchronize(m->d2h_stream));
   CFS_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (g_options.pipeline_trace) { // development aid: where the step's time goes
+    for (size_t c = 0; c < K; ++c) {
+      float tx = 0, tk = 0, td = 0;
+      cudaEventElapsedTime(&tx, m->ev_fork, m->ev_x[c]);
+      cudaEventElapsedTime(&tk, m->ev_fork, m->ev_k[c]);
+      cudaEventElapsedTime(&td, m->ev_fork, m->ev_d[c]);
+      printf("pipeline chunk %2zu: x in %.3f ms, kernel done %.3f, y out %.3f "
+             "(final after chunk %d)\n", c, tx, tk, td,
+             m->chunks[c].final_after);
+    }
+    fflush(stdout);
+  }
   return CFS_OK;
 }
 
@@ -557,11 +661,12 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
                           : (size_t)m->ncols;
   const size_t ylen = m->sharded ? xlen : (size_t)m->nrows;
   PtrKind kx, ky;
-  classify(x, &kx);
-  classify(y, &ky);
+  bool px = false, py = false;
+  classify(x, &kx, &px);
+  classify(y, &ky, &py);
   if (kx == kPtrHost && ky == kPtrHost && m->symmetric && !m->chunks.empty() &&
       g_options.pipeline)
-    return spmv_host_pipelined(m, y, x);
+    return spmv_host_pipelined(m, y, x, px && py);
   const void *xd = x;
   void *yd = y;
   if (kx == kPtrHost) {

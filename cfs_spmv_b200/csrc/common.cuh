@@ -71,6 +71,12 @@ struct Options {
   int ctas_per_sm = 2;
   int hubs = 1;      // column-wise handling of hub columns of ragged matrices
   int pipeline = 1;  // overlap H2D / kernel / D2H in cfs_cuda_spmv(host, host)
+  int pipeline_trace = 0;   // print the per-chunk timeline (development aid)
+  int pipeline_graph = 1;   // replay the pipelined step as one CUDA graph
+  int pipeline_chunks = 8;  // row chunks of the pipeline (read at tune time)
+  int pipeline_skip = 0;    // measurement aid: 1 no kernels, 2 no D2H, 4 no H2D
+  int pipeline_smem = 0;    // dynamic smem of pipelined launches (occupancy cap)
+  int pipeline_ramp = 0;    // graded chunk sizes instead of equal ones (slower)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
@@ -168,7 +174,11 @@ struct cfs_matrix_s {
   };
   std::vector<Chunk> chunks;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  std::vector<cudaEvent_t> ev_x, ev_k;
+  std::vector<cudaEvent_t> ev_x, ev_k, ev_d;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaGraphExec_t pipe_graph = nullptr; // the step captured for (pipe_x, pipe_y)
+  const void *pipe_x = nullptr;
+  void *pipe_y = nullptr;
 };
 
 namespace cfsb {

@@ -472,10 +472,24 @@ int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
   m->chunks.clear();
   if (m->sharded || m->sort_window != 0 || m->nslices < 4096)
     return CFS_OK;
-  const int K = 16;
-  std::vector<long long> cut(K + 1);
-  for (int c = 0; c <= K; ++c)
-    cut[c] = m->nslices * c / K;
+  // pipeline_chunks equal chunks (8: every chunk costs ~10 us of cross-stream
+  // hand-over, tools/e2e_probe.py). pipeline_ramp = 1 grades the sizes (small
+  // first H2D / last D2H); measured slower on B200, kept as an experiment.
+  std::vector<int> weight;
+  if (g_options.pipeline_ramp)
+    weight = {1, 1, 2, 4, 8, 8, 4, 2, 1, 1};
+  else
+    weight.assign((size_t)g_options.pipeline_chunks, 1);
+  const int K = (int)weight.size();
+  long long total = 0;
+  for (int w : weight)
+    total += w;
+  std::vector<long long> cut(K + 1, 0);
+  long long acc = 0;
+  for (int c = 0; c < K; ++c) {
+    acc += weight[c];
+    cut[c + 1] = m->nslices * acc / total;
+  }
   // first row of each chunk = row tag of its first lane
   std::vector<int> row0(K + 1, m->nrows);
   for (int c = 0; c < K; ++c) {

@@ -226,13 +226,27 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
                cudaStream_t s, long long s0, long long s1) {
   const unsigned grid =
       (unsigned)(((s1 - s0) * 32 + reg::kThreads - 1) / reg::kThreads);
+  // Row chunks of the host-vector pipeline run next to PCIe copies: a kernel
+  // that saturates HBM starves the copy engines (tools/e2e_probe.py), so these
+  // launches ask for unused shared memory to cap the resident CTAs per SM.
+  int smem = 0;
+  if (!y_lower && (s0 != 0 || s1 != m->nslices) && g_options.pipeline_smem) {
+    smem = g_options.pipeline_smem;
+    static int granted = 0;
+    if (granted < smem) {
+      CFS_CUDA_TRY(cudaFuncSetAttribute(
+          reg::sym_spmv_reg_kernel<T, false>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      granted = smem;
+    }
+  }
   if (y_lower)
     reg::sym_spmv_reg_kernel<T, true><<<grid, reg::kThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
         m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
         (const T *)m->diagonal.p, xb, yb, y_lower);
   else
-    reg::sym_spmv_reg_kernel<T, false><<<grid, reg::kThreads, 0, s>>>(
+    reg::sym_spmv_reg_kernel<T, false><<<grid, reg::kThreads, smem, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
         m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
         (const T *)m->diagonal.p, xb, yb, nullptr);

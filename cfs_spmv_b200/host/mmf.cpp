@@ -41,40 +41,48 @@ struct Line {
 
 class FileImage {
 public:
-  explicit FileImage(const std::string &path) : at_(0) {
+  explicit FileImage(const std::string &path) : data_(0), size_(0), at_(0) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f)
       die("MMF file error.");
     fseek(f, 0, SEEK_END);
     long size = ftell(f);
     fseek(f, 0, SEEK_SET);
-    data_.resize(size > 0 ? (size_t)size : 0);
-    if (size > 0 && fread(&data_[0], 1, (size_t)size, f) != (size_t)size)
+    own_.resize(size > 0 ? (size_t)size : 0);
+    if (size > 0 && fread(&own_[0], 1, (size_t)size, f) != (size_t)size)
       die("MMF file error.");
     fclose(f);
+    data_ = own_.empty() ? 0 : &own_[0];
+    size_ = own_.size();
   }
+  // an image somebody else holds (the mapped file of the GPU ingest)
+  FileImage(const char *image, size_t bytes)
+      : data_(image), size_(bytes), at_(0) {}
   // next '\n'-terminated line; false when only an unterminated tail is left
   bool next(Line &l) {
-    if (at_ >= data_.size())
+    if (at_ >= size_)
       return false;
-    const char *p = &data_[at_];
-    const void *nl = memchr(p, '\n', data_.size() - at_);
+    const char *p = data_ + at_;
+    const void *nl = memchr(p, '\n', size_ - at_);
     if (!nl)
       return false;
     l.begin = p;
     l.end = (const char *)nl;
-    at_ = (size_t)(l.end - &data_[0]) + 1;
+    at_ = (size_t)(l.end - data_) + 1;
     return true;
   }
-  int peek() const { return at_ < data_.size() ? data_[at_] : -1; }
+  int peek() const { return at_ < size_ ? data_[at_] : -1; }
   void skip_line() {
     Line l;
     if (!next(l))
-      at_ = data_.size();
+      at_ = size_;
   }
+  size_t position() const { return at_; }
 
 private:
-  std::vector<char> data_;
+  const char *data_;
+  size_t size_;
+  std::vector<char> own_;
   size_t at_;
 };
 
@@ -142,8 +150,10 @@ bool DoRead(std::ifstream &in, std::vector<std::string> &arguments) {
 
 namespace detail {
 
-void scan_matrix_market(const std::string &filename, ScannedMatrix &m) {
-  FileImage file(filename);
+namespace {
+
+// banner, comments and the size line; leaves `file` at the first entry line
+void scan_header(FileImage &file, ScannedMatrix &m) {
   m.symmetric = false;
   m.col_wise = true;
   m.zero_based = false;
@@ -202,6 +212,29 @@ void scan_matrix_market(const std::string &filename, ScannedMatrix &m) {
   // the reference reads the count through its entry parser: a value, 0.42 when
   // the third token is missing, truncated to the index type
   m.nr_declared = (long)(args.size() >= 3 ? atof(args[2].c_str()) : 0.42);
+}
+
+} // namespace
+
+void scan_matrix_market_header(const char *image, size_t bytes,
+                               MmfHeader &out) {
+  FileImage file(image, bytes);
+  ScannedMatrix m;
+  scan_header(file, m);
+  out.nr_rows = m.nr_rows;
+  out.nr_cols = m.nr_cols;
+  out.nr_declared = m.nr_declared;
+  out.symmetric = m.symmetric;
+  out.col_wise = m.col_wise;
+  out.zero_based = m.zero_based;
+  out.entries_offset = file.position();
+}
+
+void scan_matrix_market(const std::string &filename, ScannedMatrix &m) {
+  FileImage file(filename);
+  scan_header(file, m);
+  std::vector<std::string> args;
+  Line line;
   const long declared = m.nr_declared;
 
   // ---- entries

@@ -38,6 +38,8 @@ extern "C" {
 #define CFS_ERR_NO_DEVICE 3 /* no CUDA device / wrong architecture           */
 #define CFS_ERR_STATE 4     /* call order (e.g. spmv before tune)            */
 #define CFS_ERR_TOO_LARGE 5 /* reference-compatible metadata infeasible      */
+#define CFS_ERR_NEEDS_HOST 6 /* input only the host loader may judge (errors
+                                the reference reports itself, > 4 GiB text)   */
 
 #define CFS_TUNING_NONE 0       /* util::Tuning::None       platform.hpp:22 */
 #define CFS_TUNING_AGGRESSIVE 1 /* util::Tuning::Aggressive platform.hpp:22 */
@@ -76,6 +78,42 @@ void cfs_cuda_host_free(void *ptr);
 int cfs_cuda_matrix_create(cfs_mat_t *out, int32_t nrows, int32_t ncols,
                            const int32_t *rowptr, const int32_t *colind,
                            const void *values, int is_double, int symmetric);
+
+/* ---- Matrix Market ingest on the GPU: replaces, for CSRMatrix(filename, ...),
+ * the loader MMF<I,V> (include/io/mmf.hpp:179-343, src/mmf.cpp:6-44) and the
+ * CSR fill (include/matrix/csr_matrix.tpp:74-107). The caller has read the
+ * banner / comment / size lines (host code, cfs_host.h); the entry lines are
+ * tokenised, converted (atoi / atof semantics, values correctly rounded like
+ * strtod), mirrored when the file is symmetric, ordered by (row, col) and
+ * turned into the full 0-based CSR on the device. The matrix owns that CSR;
+ * cfs_cuda_matrix_tune consumes it like one made by cfs_cuda_matrix_create.
+ * `symmetric` is the caller's wish (Format::sss); a general file quietly gives
+ * plain CSR (csr_matrix.tpp:13-15). Returns CFS_ERR_NEEDS_HOST for anything
+ * the reference reports as a fatal input error: the host loader then prints
+ * the reference's message. */
+typedef struct cfs_mmf_text {
+  const char *text;       /* file image in host memory                        */
+  size_t bytes;
+  size_t entries_offset;  /* first byte of the first entry line               */
+  int64_t declared;       /* entry lines announced by the size line           */
+  int32_t nrows, ncols;
+  int32_t file_symmetric; /* banner: symmetric -> mirror off-diagonal entries */
+  int32_t zero_based;     /* banner token base-0                              */
+} cfs_mmf_text;
+typedef struct cfs_mmf_report {
+  int64_t nnz;        /* expanded entry count = CSRMatrix::nnz()              */
+  int64_t host_lines; /* lines handed to the host's strtol / strtod           */
+  float ms_upload, ms_parse, ms_sort, ms_build; /* device time per phase      */
+} cfs_mmf_report;
+int cfs_cuda_matrix_create_from_mmf(cfs_mat_t *out, const cfs_mmf_text *in,
+                                    int is_double, int symmetric,
+                                    cfs_mmf_report *report);
+/* The full CSR of a matrix back to the host (CSRMatrix::rowptr() / colind() /
+ * values(), include/matrix/csr_matrix.hpp:73-75). NULL destinations are
+ * skipped. CFS_ERR_STATE once tune() has released the full CSR of a symmetric
+ * matrix (csr_matrix.tpp:1700-1706). */
+int cfs_cuda_matrix_download_csr(cfs_mat_t m, int32_t *rowptr, int32_t *colind,
+                                 void *values);
 
 /* Multi-GPU row shard: this GPU owns global rows [row_begin, row_end) of an
  * (global_nrows x global_nrows) symmetric matrix (the reference's thread

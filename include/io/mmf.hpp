@@ -40,6 +40,16 @@ struct ScannedMatrix {
 // Reads and expands `filename`. Fatal problems print the reference's message
 // on stdout and exit(1).
 void scan_matrix_market(const std::string &filename, ScannedMatrix &out);
+// Only the banner, comment and size lines of a file image (same checks, same
+// fatal messages); entries_offset is where the entry lines start. The GPU
+// ingest of CSRMatrix(filename) takes over from there.
+struct MmfHeader {
+  long nr_rows, nr_cols, nr_declared;
+  bool symmetric, col_wise, zero_based;
+  size_t entries_offset;
+};
+void scan_matrix_market_header(const char *image, size_t bytes,
+                               MmfHeader &out);
 } // namespace detail
 
 template <typename IndexType, typename ValueType> class MMF {

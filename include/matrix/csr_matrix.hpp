@@ -3,6 +3,10 @@
 // full CSR on the host; tune() hands it to the GPU through the C ABI
 // (include/cfs_cuda.h), where the lower triangle is extracted, partitioned,
 // coloured and laid out for the sm_100a kernels.
+// A matrix built from a Matrix Market file is ingested ON the GPU when one is
+// present (cfs_cuda_matrix_create_from_mmf): its full CSR then lives in HBM
+// and the host copy behind rowptr() / colind() / values() is only made when
+// one of them is called.
 #ifndef CSR_MATRIX_HPP
 #define CSR_MATRIX_HPP
 
@@ -58,9 +62,18 @@ public:
 
   // The host CSR. Like the reference, a file-constructed symmetric matrix
   // releases it during tune(): these return nullptr afterwards.
-  IndexT *rowptr() const { return rowptr_; }
-  IndexT *colind() const { return colind_; }
-  ValueT *values() const { return values_; }
+  IndexT *rowptr() const {
+    fetch_host_csr();
+    return rowptr_;
+  }
+  IndexT *colind() const {
+    fetch_host_csr();
+    return colind_;
+  }
+  ValueT *values() const {
+    fetch_host_csr();
+    return values_;
+  }
 
   // The C ABI handle behind this matrix (nullptr before tune()); lets a
   // device-side caller (a solver loop) use cfs_cuda_spmv_async directly.
@@ -71,12 +84,15 @@ private:
   int nrows_, ncols_, nnz_;
   bool symmetric_, hybrid_, owns_data_, tuned_;
   int nparts_; // CFS_NUM_THREADS when the object was built
-  IndexT *rowptr_;
-  IndexT *colind_;
-  ValueT *values_;
+  mutable IndexT *rowptr_;
+  mutable IndexT *colind_;
+  mutable ValueT *values_;
   cfs_matrix_s *device_;
+  mutable bool host_csr_pending_; // the full CSR is in HBM only (GPU ingest)
 
   void release_host_csr();
+  void fetch_host_csr() const;
+  bool ingest_on_gpu(const string &filename, bool symmetric);
 };
 
 } // namespace sparse

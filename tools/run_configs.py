@@ -31,7 +31,8 @@ def time_matrix(name, n, rp, ci, v, is_double, iters=50):
            "sort_window": inf["sort_window"], "hub_columns": inf["hub_columns"],
            "hub_entries": inf["hub_entries"], "nslices": inf["nslices"],
            "tune_s": round(tune_s, 3)}
-    for variant in (1, 5):
+    variants = [int(v) for v in os.environ.get("RUN_VARIANTS", "1,5").split(",")]
+    for variant in variants:
         capi.set_option("spmv_variant", variant)
         A.spmv_timed(y, x, 3)
         tot, kern = A.spmv_timed(y, x, iters)
