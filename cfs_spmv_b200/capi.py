@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libcfs_cuda.so")
 CFS_OK = 0
 CFS_ERR_CUDA, CFS_ERR_INVALID, CFS_ERR_NO_DEVICE, CFS_ERR_STATE, \
     CFS_ERR_TOO_LARGE = 1, 2, 3, 4, 5
+CFS_ERR_NEEDS_HOST = 6
 
 META = {
     "row_split": 1, "part_nnz_low": 2, "lower_rowptr": 3, "lower_colind": 4,
@@ -30,9 +31,10 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_device_count", "cfs_cuda_init", "cfs_cuda_last_error",
     "cfs_cuda_version", "cfs_cuda_set_option", "cfs_cuda_host_alloc", "cfs_cuda_host_free",
     "cfs_cuda_matrix_create", "cfs_cuda_matrix_create_shard",
+    "cfs_cuda_matrix_create_from_mmf", "cfs_cuda_matrix_download_csr",
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
     "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_halo_async",
-    "cfs_cuda_spmv_timed",
+    "cfs_cuda_spmv_timed", "cfs_cuda_cg_solve",
     "cfs_cuda_matrix_export",
     "cfs_gen_host_count", "cfs_gen_host_fill", "cfs_gen_host_x",
     "cfs_cuda_gen_count", "cfs_cuda_gen_fill", "cfs_cuda_gen_x",
@@ -99,6 +101,55 @@ class MatrixInfo(ctypes.Structure):
 _lib = None
 
 
+class MmfText(ctypes.Structure):
+    """cfs_mmf_text of include/cfs_cuda.h"""
+    _fields_ = [("text", ctypes.c_void_p), ("bytes", ctypes.c_size_t),
+                ("entries_offset", ctypes.c_size_t),
+                ("declared", ctypes.c_int64),
+                ("nrows", ctypes.c_int32), ("ncols", ctypes.c_int32),
+                ("file_symmetric", ctypes.c_int32),
+                ("zero_based", ctypes.c_int32)]
+
+
+class MmfReport(ctypes.Structure):
+    """cfs_mmf_report of include/cfs_cuda.h"""
+    _fields_ = [("nnz", ctypes.c_int64), ("host_lines", ctypes.c_int64),
+                ("ms_upload", ctypes.c_float), ("ms_parse", ctypes.c_float),
+                ("ms_sort", ctypes.c_float), ("ms_build", ctypes.c_float)]
+
+
+class CgResult(ctypes.Structure):
+    """cfs_cg_result of include/cfs_cuda.h"""
+    _fields_ = [("iterations", ctypes.c_int32), ("executed", ctypes.c_int32),
+                ("converged", ctypes.c_int32), ("breakdown", ctypes.c_int32),
+                ("initial_residual_norm", ctypes.c_double),
+                ("residual_norm", ctypes.c_double),
+                ("ms_total", ctypes.c_float)]
+
+
+class HostMmfHeader(ctypes.Structure):
+    """cfs_host_mmf_header of include/cfs_host.h"""
+    _fields_ = [("nrows", ctypes.c_int64), ("ncols", ctypes.c_int64),
+                ("declared", ctypes.c_int64), ("symmetric", ctypes.c_int32),
+                ("col_wise", ctypes.c_int32), ("zero_based", ctypes.c_int32),
+                ("entries_offset", ctypes.c_uint64)]
+
+
+_host_lib = None
+
+
+def host_lib():
+    """libsparse.so: the host side (Matrix Market header scan, C++ API)"""
+    global _host_lib
+    if _host_lib is None:
+        path = os.path.join(os.path.dirname(LIB_PATH), "libsparse.so")
+        L = ctypes.CDLL(path)
+        L.cfs_host_scan_mmf_header.argtypes = [
+            ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(HostMmfHeader)]
+        _host_lib = L
+    return _host_lib
+
+
 def lib():
     global _lib
     if _lib is not None:
@@ -123,6 +174,10 @@ def lib():
     L.cfs_cuda_matrix_create_shard.argtypes = [ctypes.POINTER(vp), i32, i32,
                                                i32, vp, vp, vp, ctypes.c_int]
     L.cfs_cuda_matrix_tune.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    L.cfs_cuda_matrix_create_from_mmf.argtypes = [
+        ctypes.POINTER(vp), ctypes.POINTER(MmfText), ctypes.c_int,
+        ctypes.c_int, ctypes.POINTER(MmfReport)]
+    L.cfs_cuda_matrix_download_csr.argtypes = [vp, vp, vp, vp]
     L.cfs_cuda_matrix_destroy.argtypes = [vp]
     L.cfs_cuda_matrix_destroy.restype = None
     L.cfs_cuda_matrix_info.argtypes = [vp, ctypes.POINTER(MatrixInfo)]
@@ -134,6 +189,8 @@ def lib():
                                       ctypes.POINTER(ctypes.c_float)]
     L.cfs_cuda_matrix_export.argtypes = [vp, ctypes.c_int, vp, sz,
                                          ctypes.POINTER(sz)]
+    L.cfs_cuda_cg_solve.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_double,
+                                    ctypes.POINTER(CgResult), vp, ctypes.c_int]
     gs = ctypes.POINTER(GenSpec)
     L.cfs_gen_host_count.argtypes = [gs, i64, i64, vp]
     L.cfs_gen_host_fill.argtypes = [gs, i64, i64, vp, vp, vp, ctypes.c_int]
@@ -205,6 +262,40 @@ class Matrix:
         return cls(n, n, rowptr, colind, values, values.dtype == np.float64,
                    symmetric)
 
+    @classmethod
+    def from_mmf(cls, path, is_double=True, symmetric=True):
+        """CSRMatrix(filename) with the entries parsed on the GPU: header on
+        the host (cfs_host_scan_mmf_header), the rest by
+        cfs_cuda_matrix_create_from_mmf. Returns (matrix, header, report);
+        raises CfsError(CFS_ERR_NEEDS_HOST) where the host loader must decide."""
+        image = np.fromfile(path, dtype=np.uint8)
+        h = HostMmfHeader()
+        assert host_lib().cfs_host_scan_mmf_header(
+            image.ctypes.data, image.size, ctypes.byref(h)) == 0
+        t = MmfText(image.ctypes.data, image.size, h.entries_offset,
+                    h.declared, h.nrows, h.ncols, h.symmetric, h.zero_based)
+        self = cls.__new__(cls)
+        self._h = ctypes.c_void_p()
+        self.is_double = bool(is_double)
+        self.dtype = np.float64 if is_double else np.float32
+        self._keep = None
+        rep = MmfReport()
+        check(lib().cfs_cuda_matrix_create_from_mmf(
+            ctypes.byref(self._h), ctypes.byref(t), int(is_double),
+            int(symmetric), ctypes.byref(rep)))
+        self.nrows, self.ncols = int(h.nrows), int(h.ncols)
+        report = {k: getattr(rep, k) for k, _ in MmfReport._fields_}
+        return self, h, report
+
+    def download_csr(self, nrows, nnz):
+        """the full CSR held in HBM (before tune() releases it)"""
+        rp = np.empty(nrows + 1, np.int32)
+        ci = np.empty(nnz, np.int32)
+        v = np.empty(nnz, self.dtype)
+        check(lib().cfs_cuda_matrix_download_csr(self._h, _ptr(rp), _ptr(ci),
+                                                 _ptr(v)))
+        return rp, ci, v
+
     def tune(self, nparts=1, tuning=1, allow_too_large=False):
         code = lib().cfs_cuda_matrix_tune(self._h, nparts, tuning)
         self._keep = None
@@ -232,6 +323,20 @@ class Matrix:
         check(lib().cfs_cuda_spmv_halo_async(self._h, _ptr(y_dev), _ptr(x_dev),
                                              y_lower_base, int(y_is_zero),
                                              stream))
+
+    def cg_solve(self, x, b, max_iters, rel_tol, want_history=False):
+        """A x = b by conjugate gradients on the device (cfs_cuda_cg_solve).
+        x: initial guess in, solution out (numpy or torch, host or device).
+        Returns a dict of cfs_cg_result (+ 'history' of residual norms)."""
+        res = CgResult()
+        hist = np.zeros(max_iters + 1) if want_history else None
+        check(lib().cfs_cuda_cg_solve(
+            self._h, _ptr(x), _ptr(b), int(max_iters), float(rel_tol),
+            ctypes.byref(res), _ptr(hist), max_iters + 1 if want_history else 0))
+        out = {k: getattr(res, k) for k, _ in CgResult._fields_}
+        if want_history:
+            out["history"] = hist[:res.iterations + 1]
+        return out
 
     def spmv_timed(self, y_dev, x_dev, iters, stream=0):
         """-> (total_ms, kernel_ms) summed over `iters` SpMVs"""

@@ -134,6 +134,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.pipeline_chunks = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "cg_batch") && value >= 1 && value <= 4096) {
+    g_options.cg_batch = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "diag_mode") && value >= 0 && value <= 3) {
     g_options.diag_mode = (int)value;
     return CFS_OK;

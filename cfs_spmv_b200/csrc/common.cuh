@@ -78,6 +78,7 @@ struct Options {
   int pipeline_smem = 0;    // dynamic smem of pipelined launches (occupancy cap)
   int pipeline_ramp = 0;    // graded chunk sizes instead of equal ones (slower)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
+  int cg_batch = 16; // CG iterations enqueued between two looks at the stop flag
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
 extern Options g_options;
@@ -199,12 +200,14 @@ int build_refmeta(cfs_matrix_s *m, cudaStream_t s);
 // kernels (spmv.cu)
 // ev0/ev1 (optional) are recorded directly before/after the kernel launch
 // y_lower_base: virtual base of the y vector of the GPU below (fused halo
-// reduction over NVLink) or nullptr; y_is_zero: the caller cleared y already
+// reduction over NVLink) or nullptr; y_is_zero: the caller cleared y already;
+// xdoty: kDotSlots partial sums (stride kDotStride doubles) that the kernel
+// adds x'(A x) into (the caller zeroes them), or nullptr
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     cudaStream_t s, cudaEvent_t ev0 = nullptr,
                     cudaEvent_t ev1 = nullptr, void *y_lower_base = nullptr,
                     bool y_is_zero = false, long long slice0 = 0,
-                    long long slice1 = -1);
+                    long long slice1 = -1, double *xdoty = nullptr);
 // host-vector pipeline plan (preproc.cu)
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,

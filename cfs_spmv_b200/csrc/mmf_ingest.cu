@@ -146,16 +146,22 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// *ambiguous is raised when one (row, col) occurs twice with different values:
+// the reference leaves the order of such entries to std::sort (unstable), so
+// only the host loader -- which runs the same algorithm -- can reproduce it.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     csr_from_sorted_kernel(long long nnz, int nrows,
                            const unsigned long long *__restrict__ key,
                            const double *__restrict__ val,
                            int *__restrict__ rowptr, int *__restrict__ colind,
-                           T *__restrict__ values) {
+                           T *__restrict__ values, int *__restrict__ ambiguous) {
   const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   if (i > nnz)
     return;
+  if (i > 0 && i < nnz && key[i] == key[i - 1] &&
+      __double_as_longlong(val[i]) != __double_as_longlong(val[i - 1]))
+    *ambiguous = 1;
   // rows (prev, cur] start at entry i; rows without entries repeat the offset
   const int prev = i == 0 ? -1 : (int)(key[i - 1] >> 32) - 1;
   const int cur = i == nnz ? nrows : (int)(key[i] >> 32) - 1;
@@ -222,11 +228,21 @@ int build_csr(cfs_matrix_s *m, long long nnz, const unsigned long long *key,
   CFS_TRY(m->own_rowptr.alloc((size_t)m->nrows + 1));
   CFS_TRY(m->own_colind.alloc((size_t)nnz));
   CFS_TRY(m->own_values.alloc((size_t)nnz * sizeof(T)));
+  DevArray<int> ambiguous;
+  CFS_TRY(ambiguous.alloc(1));
+  CFS_CUDA_TRY(cudaMemsetAsync(ambiguous.p, 0, 4, s));
   const unsigned grid = (unsigned)((nnz + 1 + kThreads - 1) / kThreads);
   csr_from_sorted_kernel<T><<<grid, kThreads, 0, s>>>(
       nnz, m->nrows, key, val, m->own_rowptr.p, m->own_colind.p,
-      (T *)m->own_values.p);
+      (T *)m->own_values.p, ambiguous.p);
   CFS_CUDA_TRY(cudaGetLastError());
+  int flag = 0;
+  CFS_CUDA_TRY(cudaMemcpyAsync(&flag, ambiguous.p, 4, cudaMemcpyDeviceToHost,
+                               s));
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  if (flag)
+    return needs_host("duplicate entries with different values (their order "
+                      "is std::sort's)");
   return CFS_OK;
 }
 

@@ -61,7 +61,7 @@ constexpr int kUnroll = 4;
 //
 // x and y are "virtual base" pointers: indexed by GLOBAL row/column id (for a
 // shard they point halo_begin elements before the extended local vector).
-template <typename T, int MODE, bool HALO, bool HUBS>
+template <typename T, int MODE, bool HALO, bool HUBS, bool DOT = false>
 __global__ void __launch_bounds__(kSpmvThreads)
     sym_spmv_sell_kernel(long long slice_begin, long long slice_end,
                          int row_begin,
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kSpmvThreads)
                          const T *__restrict__ sell_val,
                          const T *__restrict__ diagonal,
                          const T *__restrict__ x, T *__restrict__ y,
-                         T *__restrict__ y_lower) {
+                         T *__restrict__ y_lower, double *__restrict__ dot) {
   const int lane = threadIdx.x & 31;
   const long long s =
       slice_begin + ((blockIdx.x * (long long)kSpmvThreads + threadIdx.x) >> 5);
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kSpmvThreads)
     if (!(tag & kVrowCont))
       acc = diagonal[row - row_begin] * xr;
   }
+  const T dterm = acc;
   const int p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
   const int *cp = sell_col + (size_t)p0 * kSliceRows + lane;
   const T *vp = sell_val + (size_t)p0 * kSliceRows + lane;
@@ -138,6 +139,14 @@ __global__ void __launch_bounds__(kSpmvThreads)
   }
   if (active)
     tma::red_add(y + row, acc);
+  if (DOT) { // x'(A x), see spmv_reg.cuh
+    double c = (double)xr * (2.0 * (double)acc - (double)dterm);
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0)
+      tma::red_add(dot + (s % reg::kDotSlots) * reg::kDotStride, c);
+  }
 }
 
 // Plain CSR y = A*x, one warp per row: the comparator the reference's test
@@ -167,7 +176,8 @@ constexpr int kStages = 2; // ring depth of the persistent kernel
 
 template <typename T, int MODE>
 void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-                 cudaStream_t s, long long s0, long long s1) {
+                 cudaStream_t s, long long s0, long long s1,
+                 double *dot = nullptr) {
   const unsigned grid =
       (unsigned)(((s1 - s0) * 32 + kSpmvThreads - 1) / kSpmvThreads);
   // hub columns: flagged column stream + a second, column-wise kernel
@@ -176,16 +186,30 @@ void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   if (y_lower)
     sym_spmv_sell_kernel<T, MODE, true, false><<<grid, kSpmvThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
-        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower);
+        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower,
+        nullptr);
+  else if (hubs && dot)
+    sym_spmv_sell_kernel<T, 0, false, true, true>
+        <<<grid, kSpmvThreads, 0, s>>>(
+            s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p,
+            m->hub_colstream.p, (const T *)m->sell_val.p,
+            (const T *)m->diagonal.p, xb, yb, nullptr, dot);
   else if (hubs)
     sym_spmv_sell_kernel<T, MODE, false, true><<<grid, kSpmvThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p,
         m->hub_colstream.p, (const T *)m->sell_val.p,
-        (const T *)m->diagonal.p, xb, yb, nullptr);
+        (const T *)m->diagonal.p, xb, yb, nullptr, nullptr);
+  else if (dot)
+    sym_spmv_sell_kernel<T, 0, false, false, true>
+        <<<grid, kSpmvThreads, 0, s>>>(
+            s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
+            (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb,
+            nullptr, dot);
   else
     sym_spmv_sell_kernel<T, MODE, false, false><<<grid, kSpmvThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
-        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr);
+        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr,
+        nullptr);
   if (hubs)
     launch_hub_spmv(m, yb, xb, s);
 }
@@ -223,7 +247,8 @@ int launch_tma(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 
 template <typename T>
 int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-               cudaStream_t s, long long s0, long long s1) {
+               cudaStream_t s, long long s0, long long s1,
+               double *dot = nullptr) {
   const unsigned grid =
       (unsigned)(((s1 - s0) * 32 + reg::kThreads - 1) / reg::kThreads);
   // Row chunks of the host-vector pipeline run next to PCIe copies: a kernel
@@ -244,12 +269,17 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
     reg::sym_spmv_reg_kernel<T, true><<<grid, reg::kThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
         m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
-        (const T *)m->diagonal.p, xb, yb, y_lower);
+        (const T *)m->diagonal.p, xb, yb, y_lower, nullptr);
+  else if (dot)
+    reg::sym_spmv_reg_kernel<T, false, true><<<grid, reg::kThreads, 0, s>>>(
+        s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
+        m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
+        (const T *)m->diagonal.p, xb, yb, nullptr, dot);
   else
     reg::sym_spmv_reg_kernel<T, false><<<grid, reg::kThreads, smem, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
         m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
-        (const T *)m->diagonal.p, xb, yb, nullptr);
+        (const T *)m->diagonal.p, xb, yb, nullptr, nullptr);
   return CFS_OK;
 }
 
@@ -264,23 +294,27 @@ int launch_win(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 template <typename T>
 int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                      void *y_lower_base, cudaStream_t s, long long s0,
-                     long long s1) {
+                     long long s1, double *dot) {
   const T *xb = (const T *)x_ext - m->halo_begin;
   T *yb = (T *)y_ext - m->halo_begin;
   T *yl = (T *)y_lower_base;
   const int mode = g_options.diag_mode;
   int variant = g_options.spmv_variant;
   const bool partial = s0 != 0 || s1 != m->nslices;
-  if ((yl || partial) && variant != 1)
-    variant = 5; // halo fusion / slice ranges exist in the register kernels
+  if ((yl || partial || dot) && variant != 1)
+    variant = 5; // halo fusion / slice ranges / x'Ax exist in the register kernels
   // bulk copies of the x / y windows need 16-byte aligned vectors
   // the compressed-index kernel pays off when slices are regular; ragged
   // matrices run the generic warp-per-slice kernel (more registers, no spills)
   if (variant == 5 && m->ccol.p && mode == 0 &&
       m->nregular * 8 >= m->nslices)
-    return launch_reg<T>(m, xb, yb, yl, s, s0, s1);
-  if (variant == 5 || yl || partial)
+    return launch_reg<T>(m, xb, yb, yl, s, s0, s1, dot);
+  if (variant == 5 || yl || partial || dot)
     variant = 1;
+  if (dot) {
+    launch_sell<T, 0>(m, xb, yb, yl, s, s0, s1, dot);
+    return CFS_OK;
+  }
   if (variant >= 3 &&
       (!m->sell_slot.p || (((uintptr_t)x_ext | (uintptr_t)y_ext) & 15)))
     variant = 2;
@@ -324,7 +358,7 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1,
                     void *y_lower_base, bool y_is_zero, long long slice0,
-                    long long slice1) {
+                    long long slice1, double *xdoty) {
   if (slice1 < 0)
     slice1 = m->nslices;
   const size_t vs = m->vsize();
@@ -337,9 +371,9 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
     CFS_CUDA_TRY(cudaEventRecord(ev0, s));
   CFS_TRY(m->is_double
               ? launch_sym_typed<double>(m, y_ext, x_ext, y_lower_base, s,
-                                         slice0, slice1)
+                                         slice0, slice1, xdoty)
               : launch_sym_typed<float>(m, y_ext, x_ext, y_lower_base, s,
-                                        slice0, slice1));
+                                        slice0, slice1, xdoty));
   CFS_CUDA_TRY(cudaGetLastError());
   if (ev1)
     CFS_CUDA_TRY(cudaEventRecord(ev1, s));

@@ -50,7 +50,16 @@ constexpr int kUnroll = 4;
 
 // 8 CTAs of 256 threads per SM: the kernel is latency-bound, occupancy wins over
 // registers (measured: 275 us at 40 registers, 239 us at 32, 231 us with 128-thread CTAs)
-template <typename T, bool HALO>
+// DOT: the kernel also returns x'(A x) -- for a symmetric matrix that is
+// sum_i x_i * (2 * direct_i - d_i * x_i), and direct_i (diagonal + lower part
+// of row i times x) is exactly what the lane that owns row i holds in `acc`, so
+// the p'Ap of a conjugate-gradient step costs one warp reduction and one RED
+// per warp instead of a pass over two vectors (cg.cu). dot[] has kDotSlots
+// partial sums, 32 bytes apart, to keep same-address reductions rare.
+constexpr int kDotSlots = 128;
+constexpr int kDotStride = 4; // doubles
+
+template <typename T, bool HALO, bool DOT = false>
 __global__ void __launch_bounds__(kThreads, 16)
     sym_spmv_reg_kernel(long long slice_begin, long long slice_end,
                         int row_begin,
@@ -61,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 16)
                         const T *__restrict__ sell_val,
                         const T *__restrict__ diagonal,
                         const T *__restrict__ x, T *__restrict__ y,
-                        T *__restrict__ y_lower) {
+                        T *__restrict__ y_lower, double *__restrict__ dot) {
   const int lane = threadIdx.x & 31;
   const long long s =
       slice_begin + ((blockIdx.x * (long long)kThreads + threadIdx.x) >> 5);
@@ -78,6 +87,7 @@ __global__ void __launch_bounds__(kThreads, 16)
     if (!(tag & kVrowCont))
       acc = diagonal[row - row_begin] * xr;
   }
+  const T dterm = acc; // d_i * x_i (0 for a continuation chunk)
   const T *vp = sell_val + (size_t)p0 * kSliceRows + lane;
   const int *cp = ccol + (size_t)(cptr & ~kSliceRegular) * kSliceRows + lane;
   int w = p1 - p0;
@@ -163,6 +173,14 @@ __global__ void __launch_bounds__(kThreads, 16)
   }
   if (active)
     tma::red_add(y + row, acc);
+  if (DOT) {
+    double c = (double)xr * (2.0 * (double)acc - (double)dterm);
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0)
+      tma::red_add(dot + (s % kDotSlots) * kDotStride, c);
+  }
 }
 
 } // namespace reg

@@ -23,6 +23,22 @@ int cfs_host_load_mmf(const char *filename, int want_symmetric,
   return 0;
 }
 
+int cfs_host_scan_mmf_header(const char *image, size_t bytes,
+                             cfs_host_mmf_header *out) {
+  if (!image || !out)
+    return 2;
+  cfs::io::detail::MmfHeader h;
+  cfs::io::detail::scan_matrix_market_header(image, bytes, h);
+  out->nrows = h.nr_rows;
+  out->ncols = h.nr_cols;
+  out->declared = h.nr_declared;
+  out->symmetric = h.symmetric ? 1 : 0;
+  out->col_wise = h.col_wise ? 1 : 0;
+  out->zero_based = h.zero_based ? 1 : 0;
+  out->entries_offset = h.entries_offset;
+  return 0;
+}
+
 void cfs_host_free_csr(cfs_host_csr *m) {
   if (!m || !m->handle)
     return;

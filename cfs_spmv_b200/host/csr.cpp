@@ -332,6 +332,51 @@ void SpDMV<IndexType, ValueType>::operator()(ValueType *__restrict y,
 template struct SpDMV<int, float>;
 template struct SpDMV<int, double>;
 
+template <typename IndexType, typename ValueType>
+ConjugateGradient<IndexType, ValueType>::ConjugateGradient(
+    SparseMatrix<IndexType, ValueType> *A, Tuning t)
+    : A_(A), converged_(false), breakdown_(false), residual_norm_(0),
+      initial_residual_norm_(0), ms_(0) {
+  if (!A_->symmetric()) {
+    std::cout << "[ERROR]: ConjugateGradient needs a symmetric format "
+                 "(Format::sss) of a symmetric matrix"
+              << std::endl;
+    exit(1);
+  }
+  A_->tune(Kernel::SpDMV, t);
+}
+
+template <typename IndexType, typename ValueType>
+int ConjugateGradient<IndexType, ValueType>::operator()(
+    ValueType *__restrict x, const ValueType *__restrict b, const int N,
+    const int max_iters, const double rel_tol) {
+  assert(A_->nrows() == N);
+  CSRMatrix<IndexType, ValueType> *csr =
+      dynamic_cast<CSRMatrix<IndexType, ValueType> *>(A_);
+  if (!csr || !csr->device_handle()) {
+    std::cout << "[ERROR]: ConjugateGradient: matrix is not on the GPU"
+              << std::endl;
+    exit(1);
+  }
+  cfs_cg_result r;
+  const int status = cfs_cuda_cg_solve(csr->device_handle(), x, b, max_iters,
+                                       rel_tol, &r, nullptr, 0);
+  if (status != CFS_OK) {
+    std::cout << "[ERROR]: cfs_cuda_cg_solve: " << cfs_cuda_last_error()
+              << std::endl;
+    exit(1);
+  }
+  converged_ = r.converged != 0;
+  breakdown_ = r.breakdown != 0;
+  residual_norm_ = r.residual_norm;
+  initial_residual_norm_ = r.initial_residual_norm;
+  ms_ = r.ms_total;
+  return r.iterations;
+}
+
+template struct ConjugateGradient<int, float>;
+template struct ConjugateGradient<int, double>;
+
 } // namespace sparse
 } // namespace kernel
 } // namespace cfs

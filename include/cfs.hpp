@@ -14,5 +14,6 @@
 #include "matrix/sparse_matrix.hpp"
 #include "matrix/csr_matrix.hpp"
 #include "kernel/sparse_kernel.hpp"
+#include "kernel/cg_solver.hpp"
 
 #endif

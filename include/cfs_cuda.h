@@ -187,6 +187,29 @@ int cfs_cuda_spmv_async(cfs_mat_t m, void *y_dev, const void *x_dev,
 int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                              void *y_lower_base, int y_is_zero, void *stream);
 
+/* ---- conjugate gradients on the device: solves A x = b
+ * for a tuned symmetric positive definite matrix with the SpMV above as its
+ * only matrix operation. The reference has no solver; this is the loop its
+ * bench emulates (bench_spmv_mmf.cpp:162-167: y = A x over and over), kept in
+ * HBM: q = A p and p'q come out of ONE kernel, the vector updates are two more,
+ * an iteration is replayed as a CUDA graph and the step lengths never visit
+ * the host. x holds the initial guess on entry and the solution on return; x
+ * and b may be host or device vectors of the matrix precision. Stops when
+ * ||r_k|| <= rel_tol * ||r_0|| (recurrence residual) or after max_iters.
+ * history (optional): ||r_k|| for k = 0..iterations, at most
+ * history_capacity values. */
+typedef struct cfs_cg_result {
+  int32_t iterations; /* iterations until the stop criterion held (or max)  */
+  int32_t executed;   /* iterations enqueued (whole batches, >= iterations) */
+  int32_t converged;  /* ||r|| <= rel_tol * ||r0||                           */
+  int32_t breakdown;  /* p'Ap <= 0 met: A is not positive definite           */
+  double initial_residual_norm, residual_norm;
+  float ms_total;     /* device time of the whole solve                      */
+} cfs_cg_result;
+int cfs_cuda_cg_solve(cfs_mat_t m, void *x, const void *b, int max_iters,
+                      double rel_tol, cfs_cg_result *result, double *history,
+                      int history_capacity);
+
 /* Measurement aid for bench.py (bench_spmv_mmf.cpp:162-167 times the same
  * loop with omp_get_wtime): runs `iters` SpMVs on `stream` and returns the
  * summed device time of the SpMV KERNEL alone (kernel_ms, CUDA events placed

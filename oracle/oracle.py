@@ -41,8 +41,7 @@ def build_reference(force=False):
     /root/reference exists, i.e. in the build container)."""
     if not os.path.isdir(REFERENCE_ROOT):
         return os.path.exists(REF_TOOL)
-    if os.path.exists(REF_TOOL) and not force:
-        return True
+    # make decides what is stale (it is quick when nothing is)
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "ref_build"),
                            "-j8"])
     return os.path.exists(REF_TOOL)

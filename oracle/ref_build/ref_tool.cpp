@@ -9,6 +9,11 @@
 //       runs SparseMatrix/CSRMatrix + SpDMV exactly as bench/test do
 //       (bench/bench_spmv_mmf.cpp:100-167, test/test_spmv_mmf.cpp:54-89) and
 //       writes the private preprocessing metadata plus y to <out.bin>.
+//   ref_tool dumpcsr <input> <P> <d|s> <xseed> <out.bin> <A|N>
+//       the NON-symmetric path (Format::csr): array ctor with symmetric=false,
+//       tune(Aggressive -> partition_by_nnz, csr_matrix.tpp:438-541 | None ->
+//       partition_by_nrows, :404-435), cpu_mv / cpu_mv_serial (:2665-2704);
+//       writes row_split_ and y.
 //   ref_tool bench <input> <P> <d|s> <xseed> <loops>
 //       times the CFS SpMV like bench_spmv_mmf.cpp:145-168 and prints one
 //       JSON line.
@@ -287,6 +292,44 @@ int do_dump(const std::string &input, int P, uint64_t xseed, const char *out) {
 }
 
 template <typename V>
+int do_dump_csr(const std::string &input, int P, uint64_t xseed,
+                const char *out, bool aggressive) {
+  std::vector<std::string> a = split_colon(input);
+  HostCsr host;
+  if (a[0] == "csr")
+    load_csr_bin(input.substr(4), host);
+  else
+    generate(a, host);
+  std::vector<V> values(host.values.begin(), host.values.end());
+  CSRMatrix<int, V> A(host.rowptr.data(), host.colind.data(), values.data(),
+                      host.nrows, host.ncols, /*symmetric=*/false);
+  const int M = A.nrows(), N = A.ncols();
+  V *x = (V *)internal_alloc(N * sizeof(V));
+  V *y = (V *)internal_alloc(M * sizeof(V));
+  for (int i = 0; i < N; ++i)
+    x[i] = (V)cfs_gen_x(xseed, i);
+  for (int i = 0; i < M; ++i)
+    y[i] = (V)-7;
+  SpDMV<int, V> fn(&A, aggressive ? Tuning::Aggressive : Tuning::None);
+  fn(y, M, x, N);
+  fn(y, M, x, N);
+  Writer w(out);
+  w.scalar("nrows", M);
+  w.scalar("ncols", N);
+  w.scalar("nnz_full", A.nnz());
+  w.scalar("P", P);
+  w.scalar("aggressive", aggressive ? 1 : 0);
+  w.scalar("size_bytes", (long long)A.size());
+  w.scalar("is_double", sizeof(V) == 8);
+  if (A.row_split_)
+    w.i32("row_split", A.row_split_, P + 1);
+  w.real("y", std::vector<V>(y, y + M));
+  internal_free(x);
+  internal_free(y);
+  return 0;
+}
+
+template <typename V>
 int do_bench(const std::string &input, int P, uint64_t xseed, size_t loops) {
   double t0 = omp_get_wtime();
   Run<V> r;
@@ -352,6 +395,11 @@ int main(int argc, char **argv) {
   if (cmd == "dump")
     return dp ? do_dump<double>(input, P, xseed, argv[6])
               : do_dump<float>(input, P, xseed, argv[6]);
+  if (cmd == "dumpcsr") {
+    const bool aggressive = argc < 8 || argv[7][0] == 'A';
+    return dp ? do_dump_csr<double>(input, P, xseed, argv[6], aggressive)
+              : do_dump_csr<float>(input, P, xseed, argv[6], aggressive);
+  }
   if (cmd == "bench")
     return dp ? do_bench<double>(input, P, xseed, (size_t)atoll(argv[6]))
               : do_bench<float>(input, P, xseed, (size_t)atoll(argv[6]));

@@ -92,6 +92,29 @@ template <typename V> static int run(const string &file, Format fmt) {
     cout << "array ctor: " << (ok ? "PASSED!" : "FAILED!") << endl;
     failures += !ok;
   }
+  // 3. the solver loop on top of the same matrix: A z = (A x) gives z = x
+  if (was_symmetric) {
+    const bool dp = sizeof(V) == 8;
+    V *z = (V *)internal_alloc(N * sizeof(V));
+    for (int i = 0; i < N; ++i)
+      z[i] = (V)0;
+    ConjugateGradient<int, V> cg(A);
+    const int its = cg(z, y_csr, N, 5000, dp ? 1e-12 : 1e-6);
+    if (cg.breakdown()) {
+      cout << "cg: SKIPPED (matrix is not positive definite)" << endl;
+    } else {
+      double num = 0, den = 0;
+      for (int i = 0; i < N; ++i) {
+        num += ((double)z[i] - x[i]) * ((double)z[i] - x[i]);
+        den += (double)x[i] * x[i];
+      }
+      ok = cg.converged() && sqrt(num / den) <= (dp ? 1e-8 : 1e-3);
+      cout << "cg (" << its << " iterations, error " << sqrt(num / den)
+           << "): " << (ok ? "PASSED!" : "FAILED!") << endl;
+      failures += !ok;
+    }
+    internal_free(z);
+  }
   cout << "size(MB): " << A->size() / (float)(1024 * 1024)
        << " threads: " << get_num_threads() << endl;
   delete A;

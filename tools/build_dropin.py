@@ -6,9 +6,10 @@ GPU box):
       bench/bench_spmv_mmf.cpp, compiled where they lie under /root/reference
       against THIS repo's include/ and libsparse.so (only where the reference
       tree exists; nothing is copied);
-  api_consumer
-      this repo's own consumer of the same API (tests/cpp/api_consumer.cpp),
-      always built.
+  api_consumer, load_timer
+      this repo's own consumers of the same API (tests/cpp/*.cpp), always
+      built; load_timer is also linked against the unmodified reference by
+      oracle/ref_build/Makefile.
 """
 import os
 import subprocess
@@ -32,6 +33,8 @@ def cc(src, out, defs=()):
 def main():
     os.makedirs(OUT, exist_ok=True)
     cc(os.path.join(ROOT, "tests", "cpp", "api_consumer.cpp"), "api_consumer",
+       ["-DCFS_ENABLE_DP"])
+    cc(os.path.join(ROOT, "tests", "cpp", "load_timer.cpp"), "load_timer",
        ["-DCFS_ENABLE_DP"])
     if os.path.isdir(REF):
         cc(os.path.join(REF, "test", "test_spmv_mmf.cpp"), "test_spmv_mmf",
