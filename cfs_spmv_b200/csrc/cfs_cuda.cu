@@ -134,6 +134,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.pipeline_chunks = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "csr_layout") && (value == 0 || value == 1)) {
+    g_options.csr_layout = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "cg_batch") && value >= 1 && value <= 4096) {
     g_options.cg_batch = (int)value;
     return CFS_OK;
@@ -333,7 +337,7 @@ int cfs_cuda_matrix_create_shard(cfs_mat_t *out, int32_t global_nrows,
 }
 
 int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
-  (void)tuning; // Tuning only selects the CPU partitioner for CSR (:250-254)
+  // Tuning only selects the partitioner of a NON-symmetric matrix (:250-254)
   if (!m)
     return CFS_ERR_INVALID;
   if (m->tuned) {
@@ -368,6 +372,7 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
                               cudaMemcpyDeviceToDevice));
       m->csr_values = m->own_values.p;
     }
+    CFS_TRY(tune_csr(m, nparts, tuning, m->stream));
   } else {
     if (!m->sharded && m->nrows != m->ncols) {
       set_error("symmetric matrix must be square");
@@ -484,6 +489,8 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
                               2 * (int64_t)m->nrows * vs;
   } else {
     info->size_bytes = ((int64_t)m->nrows + 1) * 4 + m->nnz_full * (4 + vs);
+    if (m->part_by_nnz)
+      info->size_bytes += ((int64_t)m->nparts + 1) * 4; // row_split_, :223-224
     info->algorithmic_bytes = info->size_bytes + 2 * (int64_t)m->nrows * vs;
   }
   info->device_bytes =
@@ -749,8 +756,9 @@ static int copy_out(const void *dev, size_t n, size_t elem, void *dst,
 
 int cfs_cuda_matrix_export(cfs_mat_t m, int what, void *dst, size_t cap,
                            size_t *count) {
-  if (!m || !m->tuned || !m->symmetric) {
-    set_error("cfs_cuda_matrix_export: needs a tuned symmetric matrix");
+  if (!m || !m->tuned || (!m->symmetric && what != CFS_META_ROW_SPLIT)) {
+    set_error("cfs_cuda_matrix_export: needs a tuned symmetric matrix (a "
+              "non-symmetric one only has row_split)");
     return CFS_ERR_STATE;
   }
   CFS_CUDA_TRY(cudaSetDevice(m->device));

@@ -78,6 +78,7 @@ struct Options {
   int pipeline_smem = 0;    // dynamic smem of pipelined launches (occupancy cap)
   int pipeline_ramp = 0;    // graded chunk sizes instead of equal ones (slower)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
+  int csr_layout = 1; // Format::csr streams the sliced layout (0: warp per row)
   int cg_batch = 16; // CG iterations enqueued between two looks at the stop flag
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
@@ -156,6 +157,7 @@ struct cfs_matrix_s {
   // reference-compatible metadata for P partitions
   int32_t nparts = 1, ncolors = 0, nranges = 0, nblk = 0;
   bool refmeta = false;
+  bool part_by_nnz = false; // non-symmetric: row_split came from partition_by_nnz
   int64_t nedges = 0;
   std::vector<int32_t> row_split;     // P+1 (host)
   cfsb::DevArray<int32_t> weight, adj_ptr, adj, color_first, color;
@@ -187,6 +189,13 @@ namespace cfsb {
 // preprocessing (preproc.cu)
 int build_lower(cfs_matrix_s *m, cudaStream_t s);
 int build_layout(cfs_matrix_s *m, cudaStream_t s);
+int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
+                      const int32_t *src_colind, const void *src_values,
+                      int64_t src_nnz, cudaStream_t s);
+// the non-symmetric path, Format::csr (csr_path.cu)
+int tune_csr(cfs_matrix_s *m, int nparts, int tuning, cudaStream_t s);
+int launch_csr_sell(const cfs_matrix_s *m, void *y, const void *x,
+                    cudaStream_t s);
 // x / y windows of the tiles (windows.cu)
 int build_windows(cfs_matrix_s *m, cudaStream_t s);
 // index-stream compression of regular slices (compress.cu)

@@ -319,6 +319,15 @@ int build_lower(cfs_matrix_s *m, cudaStream_t s) {
 }
 
 int build_layout(cfs_matrix_s *m, cudaStream_t s) {
+  return build_layout_from(m, m->low_rowptr.p, m->low_colind.p,
+                           m->low_values.p, m->nnz_low, s);
+}
+
+// rowptr / colind / values: the CSR the layout is cut from -- the lower
+// triangle for a symmetric matrix, the full CSR for Format::csr (csr_path.cu)
+int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
+                      const int32_t *src_colind, const void *src_values,
+                      int64_t src_nnz, cudaStream_t s) {
   const int n = m->nrows;
   // virtual rows
   DevArray<int> nv, voff;
@@ -326,7 +335,7 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
   CFS_TRY(voff.alloc((size_t)n + 1));
   CFS_CUDA_TRY(cudaMemsetAsync(nv.p, 0, ((size_t)n + 1) * 4, s));
   if (n > 0)
-    count_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(n, m->low_rowptr.p,
+    count_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(n, src_rowptr,
                                                           nv.p);
   CFS_CUDA_TRY(cudaGetLastError());
   CFS_TRY(exclusive_scan_i32(nv.p, voff.p, (size_t)n + 1, s));
@@ -341,7 +350,7 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
   CFS_TRY(vlen.alloc(nlanes));
   if (n > 0)
     fill_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(
-        n, m->row_begin, m->low_rowptr.p, voff.p, m->vrow_row.p, vstart.p,
+        n, m->row_begin, src_rowptr, voff.p, m->vrow_row.p, vstart.p,
         vlen.p);
   CFS_CUDA_TRY(cudaGetLastError());
   // slice widths -> slice_ptr; if the natural order pads too much, sort the
@@ -362,8 +371,8 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
                                (size_t)m->nslices + 1, s));
     CFS_CUDA_TRY(cudaMemcpy(&total_width, m->slice_ptr.p + m->nslices, 4,
                             cudaMemcpyDeviceToHost));
-    const double padding = m->nnz_low > 0 ? (double)total_width * kSliceRows /
-                                                (double)m->nnz_low
+    const double padding = src_nnz > 0 ? (double)total_width * kSliceRows /
+                                                (double)src_nnz
                                           : 1.0;
     const double limit = attempt == 0 ? 1.15 : 1.5;
     if (padding <= limit || attempt == 2 || g_options.sort_rows == 0)
@@ -409,12 +418,12 @@ int build_layout(cfs_matrix_s *m, cudaStream_t s) {
     if (m->is_double)
       fill_sell_kernel<double><<<blocks_for(nlanes), kThreads, 0, s>>>(
           m->nvrows, m->nslices, m->slice_ptr.p, vstart.p, vlen.p,
-          m->low_colind.p, (const double *)m->low_values.p, m->vrow_row.p,
+          src_colind, (const double *)src_values, m->vrow_row.p,
           m->sell_col.p, (double *)m->sell_val.p);
     else
       fill_sell_kernel<float><<<blocks_for(nlanes), kThreads, 0, s>>>(
           m->nvrows, m->nslices, m->slice_ptr.p, vstart.p, vlen.p,
-          m->low_colind.p, (const float *)m->low_values.p, m->vrow_row.p,
+          src_colind, (const float *)src_values, m->vrow_row.p,
           m->sell_col.p, (float *)m->sell_val.p);
   }
   CFS_CUDA_TRY(cudaGetLastError());

@@ -384,6 +384,8 @@ int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,
                     cudaStream_t s) {
   if (m->nrows == 0)
     return CFS_OK;
+  if (m->sell_val.p && g_options.csr_layout) // sliced layout (csr_path.cu)
+    return launch_csr_sell(m, y, x, s);
   const unsigned grid =
       (unsigned)(((size_t)m->nrows * 32 + kSpmvThreads - 1) / kSpmvThreads);
   if (m->is_double)

@@ -66,6 +66,40 @@ void cfs_oracle_partition_by_nrows(int nrows, int P, int *row_split) {
   row_split[P] = nrows;
 }
 
+/* ---- csr_matrix.tpp:438-541, the branch of a NON-symmetric matrix
+ * (:504-515) and the tail (:517-530). The reference's "fill the last split"
+ * step may write row_split_[nthreads+1] (one int past its allocation,
+ * :518-520); only entries 0..P exist here. */
+void cfs_oracle_partition_by_nnz(int nrows, int P, const int *rowptr,
+                                 int *row_split) {
+  if (P == 1) {
+    row_split[0] = 0;
+    row_split[1] = nrows;
+    return;
+  }
+  const int nnz_per_split = rowptr[nrows] / P;
+  int curr_nnz = 0, split_cnt = 0;
+  row_split[0] = 0;
+  for (int i = 0; i < nrows; ++i) {
+    curr_nnz += rowptr[i + 1] - rowptr[i];
+    if (curr_nnz >= nnz_per_split && (i + 1) % BLK_FACTOR == 0) {
+      ++split_cnt;
+      if (split_cnt <= P)
+        row_split[split_cnt] = i + 1;
+      curr_nnz = 0;
+    }
+  }
+  if (curr_nnz < nnz_per_split && split_cnt <= P) {
+    ++split_cnt;
+    if (split_cnt <= P)
+      row_split[split_cnt] = nrows;
+  }
+  if (split_cnt > P)
+    row_split[P] = nrows;
+  for (int i = split_cnt + 1; i <= P; ++i)
+    row_split[i] = nrows;
+}
+
 static int cmp_u64(const void *a, const void *b) {
   uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
   return x < y ? -1 : x > y;

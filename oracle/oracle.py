@@ -69,6 +69,9 @@ def lib():
                                           ctypes.c_void_p]
         L.cfs_oracle_partition_by_nrows.argtypes = [ctypes.c_int, ctypes.c_int,
                                                     ctypes.c_void_p]
+        L.cfs_oracle_partition_by_nnz.argtypes = [ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_void_p,
+                                                  ctypes.c_void_p]
         for name in ("nrows", "P", "nnz_low", "nnz_diag", "ncolors", "nranges",
                      "nblk"):
             f = getattr(L, "cfs_oracle_" + name)
@@ -97,6 +100,32 @@ def partition_by_nrows(nrows, P):
     out = np.zeros(P + 1, dtype=np.int32)
     lib().cfs_oracle_partition_by_nrows(nrows, P, out.ctypes.data)
     return out
+
+
+def partition_by_nnz(rowptr, P):
+    """row_split_ of a NON-symmetric matrix under Tuning::Aggressive
+    (csr_matrix.tpp:438-541)"""
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    out = np.zeros(P + 1, dtype=np.int32)
+    lib().cfs_oracle_partition_by_nnz(len(rowptr) - 1, P, rowptr.ctypes.data,
+                                      out.ctypes.data)
+    return out
+
+
+def csr_spmv(rowptr, colind, values, x):
+    """cpu_mv / cpu_mv_serial (csr_matrix.tpp:2665-2704): y[i] summed in CSR
+    order with one accumulator"""
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    colind = np.ascontiguousarray(colind, np.int32)
+    values = np.ascontiguousarray(values)
+    x = np.ascontiguousarray(x, values.dtype)
+    n = len(rowptr) - 1
+    y = np.zeros(n, values.dtype)
+    lib().cfs_oracle_csr_spmv(n, rowptr.ctypes.data, colind.ctypes.data,
+                              values.ctypes.data,
+                              int(values.dtype == np.float64), y.ctypes.data,
+                              x.ctypes.data)
+    return y
 
 
 def valid_partition_count(nrows, P):
@@ -264,6 +293,15 @@ def run_ref_dump(input_spec, P, precision, xseed, out_path):
     env["OMP_NUM_THREADS"] = str(P)
     subprocess.check_call([REF_TOOL, "dump", input_spec, str(P), precision,
                            str(xseed), out_path], env=env)
+    return read_dump(out_path)
+
+
+def run_ref_dump_csr(input_spec, P, precision, xseed, out_path, tuning="A"):
+    """the reference's NON-symmetric path: row_split_ + y (ref_tool dumpcsr)"""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(P)
+    subprocess.check_call([REF_TOOL, "dumpcsr", input_spec, str(P), precision,
+                           str(xseed), out_path, tuning], env=env)
     return read_dump(out_path)
 
 

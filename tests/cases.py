@@ -104,3 +104,46 @@ TOL = {"d": 1e-12, "s": 1e-5}
 def gold_array(gold, key):
     """a dump omits arrays the reference never allocated (row_split_ at P=1)"""
     return gold[key] if key in gold.files else np.zeros(0, np.int32)
+
+
+# ---- the non-symmetric path (Format::csr): reference partition_by_nnz /
+# partition_by_nrows + cpu_mv (csr_matrix.tpp:404-541, 2665-2704) ----------
+def general_matrix(name):
+    """a NON-symmetric matrix derived from MATRICES[name]: every fifth
+    off-diagonal entry dropped (pattern no longer symmetric), values skewed"""
+    key = "general:" + name
+    if key not in _cache:
+        rp, ci, v = matrix(name)
+        n = len(rp) - 1
+        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+        h = (rows * 2654435761 + ci.astype(np.int64) * 40503) % 1000003
+        keep = (rows == ci) | (h % 5 != 0)
+        vals = v * (1.0 + (h % 17) / 16.0)
+        counts = np.bincount(rows[keep], minlength=n)
+        rp2 = np.zeros(n + 1, np.int32)
+        np.cumsum(counts, out=rp2[1:])
+        _cache[key] = (rp2, np.ascontiguousarray(ci[keep], np.int32),
+                       np.ascontiguousarray(vals[keep], np.float64))
+    return _cache[key]
+
+
+# (matrix, P, precision, tuning): A = Tuning::Aggressive (partition_by_nnz),
+# N = Tuning::None (partition_by_nrows)
+CSR_CASES = [
+    ("lap7_12", 1, "d", "A"), ("lap7_12", 4, "d", "A"), ("lap7_12", 4, "d", "N"),
+    ("lap7_12", 27, "d", "A"), ("lap27_10", 8, "d", "A"),
+    ("lap27_10", 16, "s", "A"), ("lap27_14", 43, "d", "A"),
+    ("banded_3000", 6, "d", "A"), ("banded_3000", 31, "d", "N"),
+    ("rmat_9", 2, "d", "A"), ("rmat_9", 8, "d", "A"), ("rmat_9", 8, "s", "A"),
+    ("rmat_9", 16, "d", "A"), ("ragged_333", 3, "d", "A"),
+    ("ragged_333", 5, "d", "N"), ("ragged_64", 2, "d", "A"),
+    ("ragged_64", 4, "d", "A"), ("diag_only_48", 3, "d", "A"),
+]
+
+
+def csr_case_id(case):
+    return "csr-%s-P%d-%s-%s" % case
+
+
+def csr_golden_path(case):
+    return os.path.join(GOLDEN_DIR, "csr", csr_case_id(case) + ".npz")

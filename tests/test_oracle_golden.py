@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import cases
+from cfs_spmv_b200 import gen
 from oracle import oracle
 
 
@@ -63,3 +64,22 @@ def test_oracle_against_live_reference_when_present(tmp_path):
             assert np.array_equal(d[k], md[k]), k
         assert int(d["ncolors"]) == o.ncolors
         assert o.spmv(x).tobytes() == d["y"].tobytes()
+
+
+@pytest.mark.parametrize("case", cases.CSR_CASES, ids=cases.csr_case_id)
+def test_oracle_csr_path_matches_reference(case):
+    """the NON-symmetric path: row_split_ of partition_by_nnz (Aggressive) /
+    partition_by_nrows (None) and y of cpu_mv, bitwise"""
+    name, P, prec, tuning = case
+    gold = np.load(cases.csr_golden_path(case))
+    rp, ci, v = cases.general_matrix(name)
+    dt = cases.dtype_of(prec)
+    n = len(rp) - 1
+    assert int(gold["nnz_full"]) == rp[-1]
+    if P > 1:
+        split = (oracle.partition_by_nnz(rp, P) if tuning == "A"
+                 else oracle.partition_by_nrows(n, P))
+        assert np.array_equal(split, gold["row_split"])
+    x = gen.gen_x(cases.XSEED, n, dtype=dt)
+    y = oracle.csr_spmv(rp, ci, v.astype(dt), x)
+    assert y.tobytes() == gold["y"].tobytes()
