@@ -185,7 +185,25 @@ def time_oracle_port(grid, loops):
             "kind": "port"}
 
 
-def workload_config(n_gpus):
+BANDED_ROWS_PER_GPU = 8000000   # configs[3]: 32 M rows on 4 GPUs
+BANDED = (2000, 152, 7)         # half bandwidth, lower entries per row x16, seed
+
+
+def workload_config(n_gpus, workload="lap27", nnz_full=None):
+    if workload == "banded":
+        n = BANDED_ROWS_PER_GPU * n_gpus
+        return {
+            "workload": "banded SPD matrix, %d rows, half bandwidth %d, ~9.5 "
+                        "lower entries per row at random offsets, double "
+                        "(BASELINE.json configs[3]%s)" % (
+                            n, BANDED[0],
+                            "" if n_gpus == 4 else " weak-scaling family"),
+            "rows": n, "nnz_full": nnz_full,
+            "rows_per_gpu": BANDED_ROWS_PER_GPU,
+            "partition": "contiguous row blocks, one per GPU",
+            "cache": "inputs larger than L2 (1.1 GB streamed per GPU per step "
+                     "vs 126 MB L2); no flush needed",
+        }
     nx, ny, nz = grid_for(n_gpus)
     return {
         "workload": "27-point Laplacian %dx%dx%d, double, lower triangle "
@@ -237,6 +255,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="lap27", choices=["lap27", "banded"],
+                    help="lap27: BASELINE configs[1]/[4] (the headline, default);"
+                         " banded: configs[3] family, 8 M rows per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -260,13 +281,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    nx, ny, nz = grid_for(world)
-    spec = capi.GenSpec.laplacian(27, nx, ny, nz)
-    nnz_full = lap27_nnz_full(nx, ny, nz)
+    if args.workload == "banded":
+        spec = capi.GenSpec.banded(BANDED_ROWS_PER_GPU * world, *BANDED)
+        nnz_full = None
+    else:
+        nx, ny, nz = grid_for(world)
+        spec = capi.GenSpec.laplacian(27, nx, ny, nz)
+        nnz_full = lap27_nnz_full(nx, ny, nz)
     t_setup = time.time()
     op = ShardedSpMV(spec, rank, world, is_double=True, xseed=XSEED)
     info = op.info
     setup_s = time.time() - t_setup
+    if nnz_full is None:  # generated pattern: count what the ranks hold
+        cnt = torch.tensor([info["nnz_full"]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(cnt)
+        nnz_full = int(cnt.item())
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -330,7 +360,7 @@ def main():
         achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.workload == "lap27":
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
@@ -343,7 +373,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(world), setup_s=round(setup_s, 2),
+            "config": dict(workload_config(world, args.workload, nnz_full),
+                           setup_s=round(setup_s, 2),
                            exchange=op.exchange_desc,
                            layout={k: info[k] for k in
                                    ("nnz_low", "nvrows", "nslices",
@@ -353,7 +384,11 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "frac_of_8000": achieved / 8000.0,
-                "kernel": "sym_spmv_reg_kernel<double> (variant 5: compressed "
+                "kernel": "sym_spmv_tile_kernel<double> (variant 6: transposed "
+                          "term transposed through shared memory, one coalesced "
+                          "RED per column and tile)"
+                          if info.get("transposed_tiles") else
+                          "sym_spmv_reg_kernel<double> (variant 5: compressed "
                           "index stream, shuffle-merged REDs)",
                 "kernel_ms": kernel_ms_avg,
                 "algorithmic_bytes_per_launch": alg_bytes,
@@ -364,7 +399,8 @@ def main():
                 "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                 "path": "cfs_cuda_spmv(host y, host x): pinned H2D, kernel and D2H "
-                        "overlapped in 16 row chunks"
+                        "overlapped in 8 row chunks, the step replayed as one "
+                        "CUDA graph"
                         if world == 1 else
                         "pinned H2D of x shard+halo, kernel, NCCL y halo, D2H",
             },
@@ -372,7 +408,7 @@ def main():
             "clocks": sampler.summary(w0, w1, (fb0, fb1)),
             "checksum": checksum,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "lap27":
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -24,7 +24,7 @@ OBJDIR = os.path.join(ROOT, "build", "obj")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-CUDA_SOURCES = ["cfs_cuda.cu", "preproc.cu", "windows.cu", "compress.cu", "hubs.cu",
+CUDA_SOURCES = ["cfs_cuda.cu", "preproc.cu", "windows.cu", "compress.cu", "tiles6.cu", "valindex.cu", "hubs.cu",
                 "refmeta.cu", "mmf_ingest.cu", "cg.cu", "csr_path.cu",
                 "spmv.cu", "gen.cu"]
 NVCC_FLAGS = [

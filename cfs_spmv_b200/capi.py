@@ -92,7 +92,10 @@ class MatrixInfo(ctypes.Structure):
                 ("index_rows", ctypes.c_int64),
                 ("hub_columns", ctypes.c_int64),
                 ("hub_entries", ctypes.c_int64),
-                ("sort_window", ctypes.c_int64)]
+                ("sort_window", ctypes.c_int64),
+                ("transposed_tiles", ctypes.c_int64),
+                ("tile_smem_bytes", ctypes.c_int64),
+                ("value_dictionary", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -90,7 +90,15 @@ const char *cfs_cuda_version(void) { return "cfs-b200 0.1 (sm_100a)"; }
 int cfs_cuda_set_option(const char *key, long long value) {
   if (!key)
     return CFS_ERR_INVALID;
-  if (!strcmp(key, "spmv_variant") && value >= 1 && value <= 5) {
+  if (!strcmp(key, "value_index") && (value == 0 || value == 1)) {
+    g_options.value_index = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "tile6") && (value == 0 || value == 1)) {
+    g_options.tile6 = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "spmv_variant") && value >= 1 && value <= 6) {
     g_options.spmv_variant = (int)value;
     return CFS_OK;
   }
@@ -382,6 +390,8 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
     CFS_TRY(build_layout(m, m->stream));
     CFS_TRY(build_windows(m, m->stream));
     CFS_TRY(build_compressed_cols(m, m->stream));
+    CFS_TRY(build_tiles6(m, m->stream));
+    CFS_TRY(build_value_index(m, m->stream));
     CFS_TRY(build_hubs(m, m->stream));
     CFS_TRY(build_pipeline_plan(m, m->stream));
     // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
@@ -474,6 +484,9 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
   info->hub_entries = m->hub_entries;
   info->sort_window = m->sort_window;
   info->index_rows = m->ccol_rows;
+  info->value_dictionary = m->ndict;
+  info->transposed_tiles = m->nt6;
+  info->tile_smem_bytes = (int64_t)m->t6_smem_entries * vs;
   if (m->symmetric && m->tuned) {
     // size(), csr_matrix.tpp:191-228 (including its (nrows + 1*nthreads) term)
     int64_t s = ((int64_t)m->nrows + 1LL * m->nparts) * 4;
@@ -501,7 +514,10 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
                 m->vrow_row.bytes() + m->sell_col.bytes() +
                 m->sell_val.bytes() + m->tile_rec.bytes() + m->hub_ptr.bytes() + m->hub_row.bytes() +
                 m->hub_val.bytes() + m->hub_colstream.bytes() +
-                m->hub_chunks.bytes() + m->sell_slot.bytes() + m->ccol.bytes() + m->slice_cptr.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
+                m->hub_chunks.bytes() + m->vcode.bytes() + m->vdict.bytes() +
+                m->t6_pack.bytes() +
+                m->t6_cptr.bytes() + m->t6_lo.bytes() + m->t6_ncols.bytes() +
+                m->t6_cptr_off.bytes() + m->sell_slot.bytes() + m->ccol.bytes() + m->slice_cptr.bytes() + m->weight.bytes() + m->adj_ptr.bytes() +
                 m->adj.bytes() + m->color.bytes() + m->color_first.bytes() +
                 m->range_ptr.bytes() + m->part_nranges.bytes() +
                 m->range_start.bytes() + m->range_end.bytes() +

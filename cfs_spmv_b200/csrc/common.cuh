@@ -50,6 +50,16 @@ constexpr int kHubFlag = 1 << 30; // in the row stream: transposed term is done
 constexpr int kTileSlices = 4;
 constexpr int kTileSteps = 56;
 
+// variant 6 (spmv_tile.cuh, tiles6.cu): tiles of kT6Slices slices whose
+// transposed term is transposed through shared memory
+constexpr int kT6Slices = 32;          // one warp per slice, 1024 threads
+constexpr int kT6MaxCols = 8192;       // columns a tile's window may span
+constexpr int kT6MaxSmemBytes = 96 * 1024; // products of a tile (2 CTAs per SM)
+constexpr int kMaxDict = 256; // distinct values a one-byte code can name
+// partial sums of x'(A x) written by the DOT kernels (cg.cu)
+constexpr int kDotSlots = 128;
+constexpr int kDotStride = 4; // doubles
+
 constexpr int kMaxWindows = 8;   // x / y windows per tile (variant 3)
 constexpr int kWindowBlocks = 28; // 32-column blocks of window space per tile
 
@@ -79,6 +89,8 @@ struct Options {
   int pipeline_ramp = 0;    // graded chunk sizes instead of equal ones (slower)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int csr_layout = 1; // Format::csr streams the sliced layout (0: warp per row)
+  int value_index = 1; // dictionary-coded values where <= 256 distinct (regular matrices)
+  int tile6 = 1;      // variant 6 where it applies (bounded column windows)
   int cg_batch = 16; // CG iterations enqueued between two looks at the stop flag
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
@@ -148,6 +160,18 @@ struct cfs_matrix_s {
   cfsb::DevArray<int32_t> hub_ptr, hub_row, hub_colstream;
   cfsb::DevArray<char> hub_val;
   cfsb::DevArray<int4> hub_chunks;    // {column, first entry, end entry, -}
+  // value indexing (valindex.cu): ndict == 0: values are streamed
+  int ndict = 0;
+  cfsb::DevArray<char> vdict;           // kMaxDict values of the matrix precision
+  cfsb::DevArray<unsigned char> vcode;  // padded_entries (absent when ndict == 1)
+  // variant 6: column-transposed tiles (tiles6.cu); nt6 == 0: not applicable
+  int64_t nt6 = 0;
+  int t6_smem_entries = 0;                  // products of the largest tile
+  int64_t t6_cptr_entries = 0;
+  cfsb::DevArray<unsigned> t6_pack;         // padded_entries: lcol | slot << 16
+  cfsb::DevArray<int> t6_lo, t6_ncols;      // per tile: first column, columns
+  cfsb::DevArray<long long> t6_cptr_off;    // per tile: offset into t6_cptr
+  cfsb::DevArray<unsigned short> t6_cptr;   // per tile: ncols + 1 slot offsets
   int64_t ntiles = 0;
   cfsb::DevArray<cfsb::TileRec> tile_rec;
   // variant 3: index stream rewritten to window slots / far codes
@@ -200,6 +224,10 @@ int launch_csr_sell(const cfs_matrix_s *m, void *y, const void *x,
 int build_windows(cfs_matrix_s *m, cudaStream_t s);
 // index-stream compression of regular slices (compress.cu)
 int build_compressed_cols(cfs_matrix_s *m, cudaStream_t s);
+// value dictionary + one-byte codes (valindex.cu)
+int build_value_index(cfs_matrix_s *m, cudaStream_t s);
+// column-transposed tiles of variant 6 (tiles6.cu)
+int build_tiles6(cfs_matrix_s *m, cudaStream_t s);
 // hub columns (hubs.cu)
 int build_hubs(cfs_matrix_s *m, cudaStream_t s);
 int launch_hub_spmv(const cfs_matrix_s *m, void *y, const void *x,

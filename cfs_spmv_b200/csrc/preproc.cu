@@ -377,7 +377,9 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
     const double limit = attempt == 0 ? 1.15 : 1.5;
     if (padding <= limit || attempt == 2 || g_options.sort_rows == 0)
       break;
-    const long long window = attempt == 0 ? 4096 : (long long)1 << 30;
+    // first try: sort inside the row blocks that become the tiles of variant 6
+    const long long window =
+        attempt == 0 ? kT6Slices * kSliceRows : (long long)1 << 30;
     if (nvrows / window >= (1 << 26))
       break;
     DevArray<unsigned> key, key_out;

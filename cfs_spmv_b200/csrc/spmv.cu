@@ -24,6 +24,7 @@
 #include "spmv_tma.cuh"
 #include "spmv_win.cuh"
 #include "spmv_reg.cuh"
+#include "spmv_tile.cuh"
 
 namespace cfsb {
 
@@ -265,22 +266,65 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
       granted = smem;
     }
   }
+  // value indexing (valindex.cu): 1 = dictionary + one-byte codes, 2 = one value
+  const int vi = !g_options.value_index || m->ndict == 0 ? 0
+                 : m->ndict == 1                        ? 2
+                                                        : 1;
+#define CFS_LAUNCH_REG(HALO, DOT, VI, SMEM, YL, DOTP)                          \
+  reg::sym_spmv_reg_kernel<T, HALO, DOT, VI>                                   \
+      <<<grid, reg::kThreads, SMEM, s>>>(                                      \
+          s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,               \
+          m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,                  \
+          (const T *)m->diagonal.p, xb, yb, YL, DOTP, m->vcode.p,              \
+          (const T *)m->vdict.p, m->ndict)
+#define CFS_LAUNCH_REG_VI(HALO, DOT, SMEM, YL, DOTP)                           \
+  do {                                                                         \
+    if (vi == 2)                                                               \
+      CFS_LAUNCH_REG(HALO, DOT, 2, SMEM, YL, DOTP);                            \
+    else if (vi == 1)                                                          \
+      CFS_LAUNCH_REG(HALO, DOT, 1, SMEM, YL, DOTP);                            \
+    else                                                                       \
+      CFS_LAUNCH_REG(HALO, DOT, 0, SMEM, YL, DOTP);                            \
+  } while (0)
   if (y_lower)
-    reg::sym_spmv_reg_kernel<T, true><<<grid, reg::kThreads, 0, s>>>(
-        s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
-        m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
-        (const T *)m->diagonal.p, xb, yb, y_lower, nullptr);
+    CFS_LAUNCH_REG_VI(true, false, 0, y_lower, nullptr);
   else if (dot)
-    reg::sym_spmv_reg_kernel<T, false, true><<<grid, reg::kThreads, 0, s>>>(
-        s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
-        m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
-        (const T *)m->diagonal.p, xb, yb, nullptr, dot);
+    CFS_LAUNCH_REG_VI(false, true, 0, nullptr, dot);
+  else if (smem) // occupancy-capped pipeline launches (measurement knob)
+    CFS_LAUNCH_REG(false, false, 0, smem, nullptr, nullptr);
   else
-    reg::sym_spmv_reg_kernel<T, false><<<grid, reg::kThreads, smem, s>>>(
-        s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,
-        m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,
-        (const T *)m->diagonal.p, xb, yb, nullptr, nullptr);
+    CFS_LAUNCH_REG_VI(false, false, 0, nullptr, nullptr);
+#undef CFS_LAUNCH_REG_VI
+#undef CFS_LAUNCH_REG
   return CFS_OK;
+}
+
+template <typename T, bool HALO, bool DOT>
+int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
+                    double *dot, cudaStream_t s) {
+  auto kernel = tile6::sym_spmv_tile_kernel<T, HALO, DOT>;
+  const int smem = m->t6_smem_entries * (int)sizeof(T);
+  static int granted = 0; // per instantiation
+  if (granted < smem) {
+    CFS_CUDA_TRY(cudaFuncSetAttribute(
+        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT6MaxSmemBytes));
+    granted = kT6MaxSmemBytes;
+  }
+  kernel<<<(unsigned)m->nt6, tile6::kThreads, smem, s>>>(
+      m->nslices, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->t6_pack.p,
+      (const T *)m->sell_val.p, (const T *)m->diagonal.p, m->t6_lo.p,
+      m->t6_ncols.p, m->t6_cptr_off.p, m->t6_cptr.p, xb, yb, y_lower, dot);
+  return CFS_OK;
+}
+
+template <typename T>
+int launch_tile6(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
+                 double *dot, cudaStream_t s) {
+  if (y_lower)
+    return launch_tile6_as<T, true, false>(m, xb, yb, y_lower, nullptr, s);
+  if (dot)
+    return launch_tile6_as<T, false, true>(m, xb, yb, nullptr, dot, s);
+  return launch_tile6_as<T, false, false>(m, xb, yb, nullptr, nullptr, s);
 }
 
 template <typename T>
@@ -301,6 +345,11 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   const int mode = g_options.diag_mode;
   int variant = g_options.spmv_variant;
   const bool partial = s0 != 0 || s1 != m->nslices;
+  // bounded column windows (banded / FEM orderings): products transposed
+  // through shared memory, one coalesced RED per column and tile
+  if ((variant == 5 || variant == 6) && m->nt6 > 0 && g_options.tile6 &&
+      !partial && mode == 0 && !(yl && dot))
+    return launch_tile6<T>(m, xb, yb, yl, dot, s);
   if ((yl || partial || dot) && variant != 1)
     variant = 5; // halo fusion / slice ranges / x'Ax exist in the register kernels
   // bulk copies of the x / y windows need 16-byte aligned vectors

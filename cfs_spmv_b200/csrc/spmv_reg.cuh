@@ -56,10 +56,20 @@ constexpr int kUnroll = 4;
 // the p'Ap of a conjugate-gradient step costs one warp reduction and one RED
 // per warp instead of a pass over two vectors (cg.cu). dot[] has kDotSlots
 // partial sums, 32 bytes apart, to keep same-address reductions rare.
-constexpr int kDotSlots = 128;
-constexpr int kDotStride = 4; // doubles
+using cfsb::kDotSlots;
+using cfsb::kDotStride;
 
-template <typename T, bool HALO, bool DOT = false>
+// VI (value indexing, valindex.cu): 0 = values are streamed (8 bytes/entry),
+// 1 = one byte per entry names the value in a dictionary of <= 256 distinct
+// values kept in shared memory, 2 = the lower triangle holds ONE distinct value,
+// nothing but the indices is streamed. Same bits multiplied either way.
+__device__ __forceinline__ unsigned ld_stream(const unsigned char *p) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <typename T, bool HALO, bool DOT = false, int VI = 0>
 __global__ void __launch_bounds__(kThreads, 16)
     sym_spmv_reg_kernel(long long slice_begin, long long slice_end,
                         int row_begin,
@@ -70,7 +80,18 @@ __global__ void __launch_bounds__(kThreads, 16)
                         const T *__restrict__ sell_val,
                         const T *__restrict__ diagonal,
                         const T *__restrict__ x, T *__restrict__ y,
-                        T *__restrict__ y_lower, double *__restrict__ dot) {
+                        T *__restrict__ y_lower, double *__restrict__ dot,
+                        const unsigned char *__restrict__ vcode,
+                        const T *__restrict__ vdict, int ndict) {
+  __shared__ T sdict[VI == 1 ? kMaxDict : 1];
+  T one_value = T(0);
+  if (VI == 1) {
+    for (int k = threadIdx.x; k < ndict; k += kThreads)
+      sdict[k] = vdict[k];
+    __syncthreads();
+  } else if (VI == 2) {
+    one_value = vdict[0];
+  }
   const int lane = threadIdx.x & 31;
   const long long s =
       slice_begin + ((blockIdx.x * (long long)kThreads + threadIdx.x) >> 5);
@@ -89,8 +110,17 @@ __global__ void __launch_bounds__(kThreads, 16)
   }
   const T dterm = acc; // d_i * x_i (0 for a continuation chunk)
   const T *vp = sell_val + (size_t)p0 * kSliceRows + lane;
+  const unsigned char *kp = vcode + (size_t)p0 * kSliceRows + lane;
   const int *cp = ccol + (size_t)(cptr & ~kSliceRegular) * kSliceRows + lane;
   int w = p1 - p0;
+  // the value of the entry `step` steps further down this lane's row
+  auto value_at = [&](int step) -> T {
+    if (VI == 2)
+      return one_value;
+    if (VI == 1)
+      return sdict[ld_stream(kp + (size_t)step * kSliceRows)];
+    return ld_stream(vp + (size_t)step * kSliceRows);
+  };
 
   if (cptr & kSliceRegular) {
     // lane k holds the base column of step k
@@ -109,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 16)
         a[j] = T(0);
         xc[j] = T(0);
         if (j < L) {
-          a[j] = ld_stream(vp + (size_t)(k + j) * kSliceRows);
+          a[j] = value_at(k + j);
           xc[j] = x[cbase + lane + j];
         }
       }
@@ -144,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 16)
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         c[u] = ld_stream(cp + u * kSliceRows);
-        a[u] = ld_stream(vp + u * kSliceRows);
+        a[u] = value_at(u);
       }
       T xc[kUnroll];
 #pragma unroll
@@ -159,16 +189,18 @@ __global__ void __launch_bounds__(kThreads, 16)
       }
       cp += kUnroll * kSliceRows;
       vp += kUnroll * kSliceRows;
+      kp += kUnroll * kSliceRows;
     }
     for (; w > 0; --w) {
       const int c = ld_stream(cp);
-      const T a = ld_stream(vp);
+      const T a = value_at(0);
       if (c >= 0) {
         acc += a * x[c];
         tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
       }
       cp += kSliceRows;
       vp += kSliceRows;
+      kp += kSliceRows;
     }
   }
   if (active)

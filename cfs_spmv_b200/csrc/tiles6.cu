@@ -1,0 +1,193 @@
+// tiles6.cu -- preprocessing of variant 6 (spmv_tile.cuh): for every tile of
+// kT6Slices slices, the column window it touches, the column-major slot of
+// every entry and the per-column slot offsets.
+//
+// This is the GPU counterpart of the reference's conflict analysis
+// (conflict_free_aposteriori, csr_matrix.tpp:1364-1477: which rows write which
+// y entries) done per tile instead of per thread partition: after it, every
+// transposed-term product has a private shared-memory slot and every column of
+// a tile's window is summed by exactly one thread.
+//
+// Applies when every tile's window [min column, max column] spans at most
+// kT6MaxCols columns and its products fit in kT6MaxSmemBytes of shared memory
+// (banded / FEM-like orderings). Otherwise nt6 stays 0 and the other variants
+// run.
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace cfsb {
+namespace {
+
+constexpr int kBoundsThreads = 256;
+constexpr int kSlotThreads = 1024;
+constexpr int kBinsPerThread = kT6MaxCols / kSlotThreads;
+
+__device__ __forceinline__ void tile_range(long long tile, long long nslices,
+                                           const int *slice_ptr, size_t *begin,
+                                           size_t *end) {
+  const long long s0 = tile * kT6Slices;
+  const long long s1 = s0 + kT6Slices < nslices ? s0 + kT6Slices : nslices;
+  *begin = (size_t)slice_ptr[s0] * kSliceRows;
+  *end = (size_t)slice_ptr[s1] * kSliceRows;
+}
+
+// per tile: smallest / largest column and the number of real entries
+__global__ void __launch_bounds__(kBoundsThreads)
+    tile_bounds_kernel(long long nslices, const int *__restrict__ slice_ptr,
+                       const int *__restrict__ sell_col, int *__restrict__ lo,
+                       int *__restrict__ hi, int *__restrict__ count) {
+  size_t begin, end;
+  tile_range(blockIdx.x, nslices, slice_ptr, &begin, &end);
+  int my_lo = INT_MAX, my_hi = -1, my_n = 0;
+  for (size_t e = begin + threadIdx.x; e < end; e += kBoundsThreads) {
+    const int c = sell_col[e];
+    if (c >= 0) {
+      my_lo = min(my_lo, c);
+      my_hi = max(my_hi, c);
+      ++my_n;
+    }
+  }
+  typedef cub::BlockReduce<int, kBoundsThreads> Reduce;
+  __shared__ typename Reduce::TempStorage tmp;
+  my_lo = Reduce(tmp).Reduce(my_lo, cub::Min());
+  __syncthreads();
+  my_hi = Reduce(tmp).Reduce(my_hi, cub::Max());
+  __syncthreads();
+  my_n = Reduce(tmp).Sum(my_n);
+  if (threadIdx.x == 0) {
+    lo[blockIdx.x] = my_n ? my_lo : 0;
+    hi[blockIdx.x] = my_hi;
+    count[blockIdx.x] = my_n;
+  }
+}
+
+// per tile: histogram over the window -> slot offsets (cptr) -> a slot for
+// every entry. The order of the entries of one column is the order in which
+// their atomics land: fixed once here, the same for every later SpMV.
+__global__ void __launch_bounds__(kSlotThreads)
+    tile_slots_kernel(long long nslices, const int *__restrict__ slice_ptr,
+                      const int *__restrict__ sell_col,
+                      const int *__restrict__ lo, const int *__restrict__ ncols,
+                      const long long *__restrict__ cptr_off,
+                      unsigned short *__restrict__ cptr,
+                      unsigned *__restrict__ pack) {
+  extern __shared__ int window[];
+  int *start = window;               // histogram, then exclusive offsets
+  int *cursor = window + kT6MaxCols;
+  typedef cub::BlockScan<int, kSlotThreads> Scan;
+  __shared__ typename Scan::TempStorage scan_tmp;
+  const long long tile = blockIdx.x;
+  size_t begin, end;
+  tile_range(tile, nslices, slice_ptr, &begin, &end);
+  const int base = lo[tile], W = ncols[tile];
+  for (int j = threadIdx.x; j < kT6MaxCols; j += kSlotThreads) {
+    start[j] = 0;
+    cursor[j] = 0;
+  }
+  __syncthreads();
+  for (size_t e = begin + threadIdx.x; e < end; e += kSlotThreads) {
+    const int c = sell_col[e];
+    if (c >= 0)
+      atomicAdd(&start[c - base], 1);
+  }
+  __syncthreads();
+  // exclusive scan over the window: kBinsPerThread consecutive bins per thread
+  int local[kBinsPerThread], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kBinsPerThread; ++k) {
+    local[k] = start[threadIdx.x * kBinsPerThread + k];
+    sum += local[k];
+  }
+  int offset = 0;
+  Scan(scan_tmp).ExclusiveSum(sum, offset);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kBinsPerThread; ++k) {
+    start[threadIdx.x * kBinsPerThread + k] = offset;
+    offset += local[k];
+  }
+  __syncthreads();
+  unsigned short *out = cptr + cptr_off[tile];
+  // W < kT6MaxCols and the bins beyond the window are empty: start[W] = total
+  for (int j = threadIdx.x; j <= W; j += kSlotThreads)
+    out[j] = (unsigned short)start[j];
+  for (size_t e = begin + threadIdx.x; e < end; e += kSlotThreads) {
+    const int c = sell_col[e];
+    unsigned p = 0xffffffffu;
+    if (c >= 0) {
+      const int j = c - base;
+      const int slot = start[j] + atomicAdd(&cursor[j], 1);
+      p = (unsigned)j | ((unsigned)slot << 16);
+    }
+    pack[e] = p;
+  }
+}
+
+} // namespace
+
+int build_tiles6(cfs_matrix_s *m, cudaStream_t s) {
+  m->nt6 = 0;
+  m->t6_smem_entries = 0;
+  // regular (stencil) matrices run variant 5; tiny ones gain nothing
+  if (!g_options.tile6 || m->nslices < kT6Slices ||
+      m->nregular * 8 >= m->nslices)
+    return CFS_OK;
+  const long long nt = (m->nslices + kT6Slices - 1) / kT6Slices;
+  DevArray<int> lo, hi, count;
+  CFS_TRY(lo.alloc((size_t)nt));
+  CFS_TRY(hi.alloc((size_t)nt));
+  CFS_TRY(count.alloc((size_t)nt));
+  tile_bounds_kernel<<<(unsigned)nt, kBoundsThreads, 0, s>>>(
+      m->nslices, m->slice_ptr.p, m->sell_col.p, lo.p, hi.p, count.p);
+  CFS_CUDA_TRY(cudaGetLastError());
+  std::vector<int> hlo((size_t)nt), hhi((size_t)nt), hcount((size_t)nt);
+  CFS_CUDA_TRY(cudaMemcpyAsync(hlo.data(), lo.p, (size_t)nt * 4,
+                               cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaMemcpyAsync(hhi.data(), hi.p, (size_t)nt * 4,
+                               cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaMemcpyAsync(hcount.data(), count.p, (size_t)nt * 4,
+                               cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  const int max_entries = (int)(kT6MaxSmemBytes / m->vsize());
+  std::vector<int> hncols((size_t)nt);
+  std::vector<long long> hoff((size_t)nt + 1, 0);
+  int largest = 0;
+  for (long long t = 0; t < nt; ++t) {
+    const int W = hcount[t] ? hhi[t] - hlo[t] + 1 : 0;
+    if (W > kT6MaxCols - 1 || hcount[t] > max_entries || hcount[t] > 65535)
+      return CFS_OK; // not a bounded-window matrix: the other variants run
+    hncols[t] = W;
+    hoff[t + 1] = hoff[t] + W + 1;
+    largest = hcount[t] > largest ? hcount[t] : largest;
+  }
+  CFS_TRY(m->t6_lo.alloc((size_t)nt));
+  CFS_TRY(m->t6_ncols.alloc((size_t)nt));
+  CFS_TRY(m->t6_cptr_off.alloc((size_t)nt + 1));
+  CFS_TRY(m->t6_cptr.alloc((size_t)hoff[nt]));
+  CFS_TRY(m->t6_pack.alloc((size_t)m->padded_entries));
+  CFS_CUDA_TRY(cudaMemcpyAsync(m->t6_lo.p, hlo.data(), (size_t)nt * 4,
+                               cudaMemcpyHostToDevice, s));
+  CFS_CUDA_TRY(cudaMemcpyAsync(m->t6_ncols.p, hncols.data(), (size_t)nt * 4,
+                               cudaMemcpyHostToDevice, s));
+  CFS_CUDA_TRY(cudaMemcpyAsync(m->t6_cptr_off.p, hoff.data(),
+                               ((size_t)nt + 1) * 8, cudaMemcpyHostToDevice,
+                               s));
+  const int slot_smem = 2 * kT6MaxCols * (int)sizeof(int);
+  CFS_CUDA_TRY(cudaFuncSetAttribute(tile_slots_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    slot_smem));
+  tile_slots_kernel<<<(unsigned)nt, kSlotThreads, slot_smem, s>>>(
+      m->nslices, m->slice_ptr.p, m->sell_col.p, m->t6_lo.p, m->t6_ncols.p,
+      m->t6_cptr_off.p, m->t6_cptr.p, m->t6_pack.p);
+  CFS_CUDA_TRY(cudaGetLastError());
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  m->nt6 = nt;
+  m->t6_smem_entries = largest;
+  m->t6_cptr_entries = hoff[nt];
+  return CFS_OK;
+}
+
+} // namespace cfsb

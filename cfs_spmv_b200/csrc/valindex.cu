@@ -1,0 +1,205 @@
+// valindex.cu -- value indexing of the lower triangle (lossless).
+//
+// Stencil and graph matrices repeat a handful of values: the 27-point Laplacian
+// of BASELINE configs[1] has ONE off-diagonal value, -1. Streaming 8 bytes per
+// entry for it is 68 % of the kernel's HBM traffic. When the lower triangle
+// holds at most kMaxDict distinct values (compared BIT for bit: -0.0 and 0.0,
+// every NaN payload are different values) the value stream is replaced by
+//   vdict : the distinct values, ascending by bit pattern
+//   vcode : one byte per entry, same slice-column-major order as sell_val
+// and a single distinct value needs no code stream at all. The arithmetic of
+// the kernel does not change -- it multiplies by vdict[vcode] instead of the
+// streamed value, the very same bits -- so results are identical with and
+// without it (tests/test_gpu_parity.py). This is the value-side sibling of the
+// index compression of compress.cu (the idea is CSR-VI,
+// Kourtis, Goumas, Koziris, "Optimizing sparse matrix-vector multiplication
+// using index and value compression", CF'08).
+//
+// Build: distinct values of a sample -> dictionary -> every entry is encoded by
+// binary search; an entry outside the dictionary aborts the attempt and the
+// dictionary is rebuilt from ALL values (sort + unique) once.
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace cfsb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr long long kSample = 1 << 20;
+
+template <typename T> struct Bits;
+template <> struct Bits<double> {
+  typedef unsigned long long type;
+};
+template <> struct Bits<float> {
+  typedef unsigned int type;
+};
+
+// code of every real entry (col >= 0); padding gets code 0 (never used)
+template <typename U>
+__global__ void __launch_bounds__(kThreads)
+    encode_kernel(long long n, const U *__restrict__ val,
+                  const int *__restrict__ col, const U *__restrict__ dict,
+                  int ndict, unsigned char *__restrict__ code,
+                  int *__restrict__ missing) {
+  __shared__ U sdict[kMaxDict];
+  for (int k = threadIdx.x; k < ndict; k += kThreads)
+    sdict[k] = dict[k];
+  __syncthreads();
+  const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (i >= n)
+    return;
+  unsigned char c = 0;
+  if (col[i] >= 0) {
+    const U v = val[i];
+    int lo = 0, hi = ndict; // first k with sdict[k] >= v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sdict[mid] < v)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo < ndict && sdict[lo] == v)
+      c = (unsigned char)lo;
+    else
+      *missing = 1;
+  }
+  code[i] = c;
+}
+
+// the real entries' bit patterns, compacted, for sort + unique
+template <typename U>
+__global__ void __launch_bounds__(kThreads)
+    gather_bits_kernel(long long n, long long stride, long long count,
+                       const U *__restrict__ val, const int *__restrict__ col,
+                       U *__restrict__ out, U filler) {
+  const long long k = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (k >= count)
+    return;
+  const long long i = k * stride;
+  out[k] = (i < n && col[i] >= 0) ? val[i] : filler;
+}
+
+template <typename U>
+int distinct_values(const U *val, const int *col, long long n, long long stride,
+                    U filler, std::vector<U> &out, cudaStream_t s) {
+  const long long count = (n + stride - 1) / stride;
+  DevArray<U> keys, sorted, uniq;
+  DevArray<int> nuniq;
+  CFS_TRY(keys.alloc((size_t)count));
+  CFS_TRY(sorted.alloc((size_t)count));
+  CFS_TRY(uniq.alloc((size_t)count));
+  CFS_TRY(nuniq.alloc(1));
+  gather_bits_kernel<U><<<(unsigned)((count + kThreads - 1) / kThreads),
+                          kThreads, 0, s>>>(n, stride, count, val, col, keys.p,
+                                            filler);
+  CFS_CUDA_TRY(cudaGetLastError());
+  size_t tb = 0, tb2 = 0;
+  CFS_CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, sorted.p,
+                                              count, 0, (int)sizeof(U) * 8, s));
+  CFS_CUDA_TRY(cub::DeviceSelect::Unique(nullptr, tb2, sorted.p, uniq.p,
+                                         nuniq.p, count, s));
+  DevArray<char> tmp;
+  CFS_TRY(tmp.alloc(tb > tb2 ? tb : tb2));
+  CFS_CUDA_TRY(cub::DeviceRadixSort::SortKeys(tmp.p, tb, keys.p, sorted.p,
+                                              count, 0, (int)sizeof(U) * 8, s));
+  CFS_CUDA_TRY(cub::DeviceSelect::Unique(tmp.p, tb2, sorted.p, uniq.p, nuniq.p,
+                                         count, s));
+  int h = 0;
+  CFS_CUDA_TRY(cudaMemcpyAsync(&h, nuniq.p, 4, cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  out.clear();
+  if (h > kMaxDict + 1) // + 1: the filler may be one of them
+    return CFS_OK;      // too many: out stays empty
+  out.resize((size_t)h);
+  if (h)
+    CFS_CUDA_TRY(cudaMemcpy(out.data(), uniq.p, (size_t)h * sizeof(U),
+                            cudaMemcpyDeviceToHost));
+  return CFS_OK;
+}
+
+template <typename T> int build_typed(cfs_matrix_s *m, cudaStream_t s) {
+  typedef typename Bits<T>::type U;
+  const long long n = m->padded_entries;
+  const U *val = (const U *)m->sell_val.p;
+  const int *col = m->sell_col.p;
+  // a value that is certainly in the matrix, to stand in for padding / holes
+  U filler = 0;
+  {
+    // first real entry: slice-column-major, so look at the first slice's rows
+    std::vector<int> c(kSliceRows);
+    std::vector<U> v(kSliceRows);
+    bool found = false;
+    for (long long base = 0; base < n && !found; base += (long long)kSliceRows << 10) {
+      CFS_CUDA_TRY(cudaMemcpy(c.data(), col + base, kSliceRows * 4,
+                              cudaMemcpyDeviceToHost));
+      CFS_CUDA_TRY(cudaMemcpy(v.data(), val + base, kSliceRows * sizeof(U),
+                              cudaMemcpyDeviceToHost));
+      for (int k = 0; k < kSliceRows && !found; ++k)
+        if (c[k] >= 0) {
+          filler = v[k];
+          found = true;
+        }
+    }
+    if (!found)
+      return CFS_OK; // no entry found where we looked: leave the values alone
+  }
+  CFS_TRY(m->vcode.alloc((size_t)n));
+  DevArray<U> dict;
+  DevArray<int> missing;
+  CFS_TRY(dict.alloc(kMaxDict));
+  CFS_TRY(missing.alloc(1));
+  std::vector<U> values;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // attempt 0: a strided sample; attempt 1: every entry
+    const long long stride = attempt == 0 && n > kSample ? n / kSample : 1;
+    CFS_TRY(distinct_values<U>(val, col, n, stride, filler, values, s));
+    if (values.empty() || (int)values.size() > kMaxDict)
+      break; // more distinct values than a byte can name
+    const int nd = (int)values.size();
+    CFS_CUDA_TRY(cudaMemcpyAsync(dict.p, values.data(), (size_t)nd * sizeof(U),
+                                 cudaMemcpyHostToDevice, s));
+    CFS_CUDA_TRY(cudaMemsetAsync(missing.p, 0, 4, s));
+    encode_kernel<U><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0,
+                       s>>>(n, val, col, dict.p, nd, m->vcode.p, missing.p);
+    CFS_CUDA_TRY(cudaGetLastError());
+    int miss = 0;
+    CFS_CUDA_TRY(cudaMemcpyAsync(&miss, missing.p, 4, cudaMemcpyDeviceToHost,
+                                 s));
+    CFS_CUDA_TRY(cudaStreamSynchronize(s));
+    if (!miss) {
+      CFS_TRY(m->vdict.alloc((size_t)kMaxDict * sizeof(T)));
+      CFS_CUDA_TRY(cudaMemsetAsync(m->vdict.p, 0, kMaxDict * sizeof(T), s));
+      CFS_CUDA_TRY(cudaMemcpyAsync(m->vdict.p, values.data(),
+                                   (size_t)nd * sizeof(U),
+                                   cudaMemcpyHostToDevice, s));
+      CFS_CUDA_TRY(cudaStreamSynchronize(s));
+      m->ndict = nd;
+      if (nd == 1)
+        m->vcode.release(); // one value: nothing to index
+      return CFS_OK;
+    }
+    if (stride == 1)
+      break;
+  }
+  m->vcode.release();
+  m->ndict = 0;
+  return CFS_OK;
+}
+
+} // namespace
+
+int build_value_index(cfs_matrix_s *m, cudaStream_t s) {
+  m->ndict = 0;
+  // the value-indexed kernel is the register kernel of regular matrices
+  if (!g_options.value_index || m->padded_entries == 0 ||
+      m->nregular * 8 < m->nslices)
+    return CFS_OK;
+  return m->is_double ? build_typed<double>(m, s) : build_typed<float>(m, s);
+}
+
+} // namespace cfsb

@@ -8,6 +8,7 @@
 //   tune           :231-310  -> cfs_cuda_matrix_create + cfs_cuda_matrix_tune
 //   size           :191-228  -> cfs_cuda_matrix_info.size_bytes
 //   dense_vector_multiply    -> cfs_cuda_spmv (host or device pointers)
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -101,6 +102,13 @@ bool CSRMatrix<IndexT, ValueT>::ingest_on_gpu(const string &filename,
       nnz_ = (int)report.nnz;
       host_csr_pending_ = true;
       done = true;
+      if (getenv("CFS_GPU_INGEST_REPORT"))
+        fprintf(stderr,
+                "[ingest] %lld entries, %lld lines decided by the host; device "
+                "ms: upload %.2f parse %.2f mirror+sort %.2f csr %.2f\n",
+                (long long)report.nnz, (long long)report.host_lines,
+                report.ms_upload, report.ms_parse, report.ms_sort,
+                report.ms_build);
 #ifdef _LOG_INFO
       cout << "[INFO]: Matrix Market file parsed on the GPU: " << report.nnz
            << " entries, " << report.host_lines

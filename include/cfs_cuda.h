@@ -55,7 +55,10 @@ const char *cfs_cuda_last_error(void);
 const char *cfs_cuda_version(void);
 /* run-time tunables (the CFS_GPU_* knobs): "spmv_variant" 1 = one warp per
  * slice with direct loads, 2 = persistent TMA-staged kernel, 4 = shared-memory
- * x/y windows, 5 = compressed index stream + shuffle-merged REDs (default);
+ * x/y windows, 5 = compressed index stream + shuffle-merged REDs (default; on
+ * matrices with bounded column windows it hands over to 6 = transposed term
+ * transposed through shared memory, "tile6" 0 switches that off); "value_index" 0/1: dictionary-coded values
+ * for regular matrices with <= 256 distinct values (lossless, default 1);
  * "sort_rows", "pipeline", "hubs" 0/1;
  * "ctas_per_sm" for the persistent kernel. Returns CFS_ERR_INVALID for an
  * unknown key. */
@@ -158,6 +161,11 @@ typedef struct cfs_matrix_info {
   int64_t hub_entries;    /* lower entries in those columns                   */
   int64_t sort_window;    /* 0 = natural row order; else rows were sorted by
                              length inside windows of this many rows          */
+  int64_t transposed_tiles; /* tiles whose transposed term goes through shared
+                               memory (variant 6); 0 = variant not applicable */
+  int64_t tile_smem_bytes;  /* shared memory of the largest such tile         */
+  int64_t value_dictionary; /* distinct values of the lower triangle when the
+                               value stream is dictionary-coded (<= 256), else 0 */
 } cfs_matrix_info;
 
 int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info);

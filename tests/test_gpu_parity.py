@@ -304,13 +304,16 @@ def test_full_size_config2_properties(gpu):
     A.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 50])
 @pytest.mark.parametrize("name,prec", [("lap27_14", "d"), ("lap7_12", "s"),
                                        ("banded_3000", "d"), ("rmat_9", "d"),
                                        ("ragged_333", "d"), ("lap27_10", "s")])
 def test_every_kernel_variant_matches_the_reference(gpu, variant, name, prec):
     """1: warp per slice, 2: persistent TMA-staged, 4: shared-memory x/y
-    windows, 5 (default): compressed index stream + shuffle-merged REDs"""
+    windows, 5 (default): compressed index stream + shuffle-merged REDs,
+    handing over to 6 (products transposed through shared memory) on irregular
+    matrices with bounded column windows; 50 = variant 5 with that switched
+    off"""
     rp, ci, v = cases.matrix(name)
     dt = cases.dtype_of(prec)
     x = gen.gen_x(cases.XSEED, len(rp) - 1, dtype=dt)
@@ -319,14 +322,49 @@ def test_every_kernel_variant_matches_the_reference(gpu, variant, name, prec):
     A = capi.Matrix.from_csr(rp, ci, v.astype(dt))
     A.tune(1)
     try:
-        capi.set_option("spmv_variant", variant)
+        capi.set_option("spmv_variant", 5 if variant == 50 else variant)
+        capi.set_option("tile6", 0 if variant == 50 else 1)
         y = np.full(len(x), -3.0, dtype=dt)
         for _ in range(2):
             A.spmv(y, x)
             assert cases.normwise_rel_err(y, ref) <= cases.TOL[prec]
     finally:
         capi.set_option("spmv_variant", 5)
+        capi.set_option("tile6", 1)
         A.close()
+
+
+@pytest.mark.parametrize("prec", ["d", "s"])
+def test_transposed_tiles_on_a_banded_matrix(gpu, prec):
+    """variant 6 on the matrix family it exists for (BASELINE configs[3],
+    scaled down): applicable, same y as the oracle, same y with it off"""
+    spec = capi.GenSpec.banded(150000, 2000, 152, 7)
+    rp, ci, v = capi.gen_host_csr(spec)
+    dt = cases.dtype_of(prec)
+    n = len(rp) - 1
+    x = gen.gen_x(cases.XSEED, n, dtype=dt)
+    ref = oracle.Oracle(rp, ci, v.astype(dt), 1).spmv(x)
+    A = capi.Matrix.from_csr(rp, ci, v.astype(dt))
+    A.tune(1)
+    inf = A.info()
+    assert inf["transposed_tiles"] == (inf["nslices"] + 31) // 32
+    assert 0 < inf["tile_smem_bytes"] <= 96 * 1024
+    y = np.full(n, 5.0, dtype=dt)
+    A.spmv(y, x)
+    A.spmv(y, x)
+    assert cases.normwise_rel_err(y, ref) <= cases.TOL[prec]
+    capi.set_option("tile6", 0)
+    y0 = np.zeros(n, dtype=dt)
+    A.spmv(y0, x)
+    capi.set_option("tile6", 1)
+    assert cases.normwise_rel_err(y0, ref) <= cases.TOL[prec]
+    A.close()
+    # a matrix whose tiles span too many columns keeps the other variants
+    rp, ci, v = gen.rmat(15, 8, seed=1)
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(1)
+    assert A.info()["transposed_tiles"] == 0
+    A.close()
 
 
 def test_regular_slices_and_windows_are_found(gpu):
@@ -434,3 +472,45 @@ def test_hub_columns_run_column_wise(gpu):
         finally:
             capi.set_option("hubs", 1)
             A.close()
+
+
+@pytest.mark.parametrize("prec", ["d", "s"])
+@pytest.mark.parametrize("ndistinct", [1, 2, 3, 200, 256, 257, 100000])
+def test_value_indexing_is_lossless(gpu, prec, ndistinct):
+    """valindex.cu: <= 256 distinct lower-triangle values (compared bit for
+    bit) -> dictionary + one-byte codes; 1 value -> no value stream at all;
+    more -> values stay streamed. Same y as the oracle either way."""
+    spec = capi.GenSpec.laplacian(27, 200, 12, 8)   # regular slices
+    rp, ci, v = capi.gen_host_csr(spec)
+    n = len(rp) - 1
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    lo, hi = np.minimum(rows, ci), np.maximum(rows, ci)
+    if ndistinct > 1:   # symmetric: the value depends on the unordered pair
+        k = (lo * 7919 + hi * 104729) % ndistinct
+        table = -(1.0 + np.arange(ndistinct) / 1024.0)
+        if ndistinct == 2:
+            table = np.array([0.0, -0.0])   # equal as numbers, different bits
+        v = np.where(rows == ci, v, table[k])
+    dt = cases.dtype_of(prec)
+    v = v.astype(dt)
+    x = gen.gen_x(cases.XSEED, n, dtype=dt)
+    ref = oracle.Oracle(rp, ci, v, 1).spmv(x)
+    A = capi.Matrix.from_csr(rp, ci, v)
+    A.tune(1)
+    inf = A.info()
+    lower = v[ci < rows]
+    expect = len(np.unique(lower.view(np.uint64 if dt == np.float64
+                                      else np.uint32)))
+    assert inf["value_dictionary"] == (expect if expect <= 256 else 0)
+    y = np.full(n, 3.0, dtype=dt)
+    A.spmv(y, x)
+    A.spmv(y, x)
+    assert cases.normwise_rel_err(y, ref) <= cases.TOL[prec]
+    capi.set_option("value_index", 0)
+    y0 = np.zeros(n, dtype=dt)
+    A.spmv(y0, x)
+    capi.set_option("value_index", 1)
+    assert cases.normwise_rel_err(y0, ref) <= cases.TOL[prec]
+    # the dictionary changes which bytes are read, not what is computed
+    assert cases.normwise_rel_err(y, y0) <= (1e-15 if prec == "d" else 1e-6)
+    A.close()

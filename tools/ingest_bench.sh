@@ -24,8 +24,7 @@ for M in /tmp/lap7_100.mtx /tmp/lap27_60.mtx; do
   echo "== this library, host loader (CFS_GPU_INGEST=0)"
   CFS_GPU_INGEST=0 build/dropin/load_timer $M 1 warm
   echo "== this library, GPU ingest, CUDA context created before the clock"
-  build/dropin/load_timer $M 1 warm
-  build/dropin/load_timer $M 1 warm
+  for k in 1 2 3 4; do CFS_GPU_INGEST_REPORT=1 build/dropin/load_timer $M 1 warm; done
   echo "== this library, GPU ingest, cold process (context creation inside)"
   build/dropin/load_timer $M 1
 done

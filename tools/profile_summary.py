@@ -4,7 +4,8 @@ profiles/:  <tag>_launches.csv (verbatim launch list), <tag>_launch_shares.txt,
 <tag>_<kernel>_hot_sass.txt (stall samples per SASS line) and traffic.json
 (DRAM bytes per launch, read by bench.py).
 
-usage: python tools/profile_summary.py <tag> <launches.csv> <prof.ncu-rep> <kernel-short-name>
+usage: python tools/profile_summary.py <tag> <launches.csv> <prof.ncu-rep> <kernel-short-name> [traffic-file]
+(traffic-file defaults to traffic.json, the one bench.py reads for the headline kernel)
 """
 import collections
 import csv
@@ -50,7 +51,7 @@ def launches(tag, path):
                 n, t, 100 * t / tot, t / n, k[:110]))
 
 
-def details(tag, rep, kname):
+def details(tag, rep, kname, traffic_name="traffic.json"):
     rows = list(csv.reader(io.StringIO(ncu_page(rep, "details"))))
     h = rows[0]
     keep = [r for r in rows[1:] if r[h.index("ID")] == "0"]
@@ -86,7 +87,7 @@ def details(tag, rep, kname):
         "per_launch": per,
         "source": "ncu --set full --clock-control none, %s" % os.path.basename(rep),
     }
-    json.dump(t, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+    json.dump(t, open(os.path.join(OUT, traffic_name), "w"), indent=1)
     # hot SASS
     src = list(csv.reader(io.StringIO(ncu_page(rep, "source"))))
     for idx, r in enumerate(src[:10]):
@@ -122,8 +123,9 @@ def details(tag, rep, kname):
 
 if __name__ == "__main__":
     tag, lpath, rep, kname = sys.argv[1:5]
+    traffic_name = sys.argv[5] if len(sys.argv) > 5 else "traffic.json"
     os.makedirs(OUT, exist_ok=True)
     launches(tag, lpath)
-    details(tag, rep, kname)
+    details(tag, rep, kname, traffic_name)
     print(open(os.path.join(OUT, tag + "_launch_shares.txt")).read()[:1500])
-    print(open(os.path.join(OUT, "traffic.json")).read()[:600])
+    print(open(os.path.join(OUT, traffic_name)).read()[:600])

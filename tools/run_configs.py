@@ -29,11 +29,14 @@ def time_matrix(name, n, rp, ci, v, is_double, iters=50):
            "padding": inf["padded_entries"] / max(inf["nnz_low"], 1),
            "regular_slices": inf["regular_slices"],
            "sort_window": inf["sort_window"], "hub_columns": inf["hub_columns"],
+           "transposed_tiles": inf["transposed_tiles"],
+           "tile_smem_bytes": inf["tile_smem_bytes"],
            "hub_entries": inf["hub_entries"], "nslices": inf["nslices"],
            "tune_s": round(tune_s, 3)}
     variants = [int(v) for v in os.environ.get("RUN_VARIANTS", "1,5").split(",")]
     for variant in variants:
-        capi.set_option("spmv_variant", variant)
+        capi.set_option("spmv_variant", 5 if variant == 50 else variant)
+        capi.set_option("tile6", 0 if variant == 50 else 1)
         A.spmv_timed(y, x, 3)
         tot, kern = A.spmv_timed(y, x, iters)
         us = kern / iters * 1e3

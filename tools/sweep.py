@@ -26,7 +26,9 @@ def main():
     y = torch.zeros_like(x)
     ref = None
     configs = [("v1", 1, 2, 0), ("v2 ctas=4", 2, 4, 0), ("v3 ctas=2", 3, 2, 0),
-               ("v3 ctas=3", 3, 3, 0), ("v4", 4, 1, 0), ("v5", 5, 1, 0)]
+               ("v3 ctas=3", 3, 3, 0), ("v4", 4, 1, 0), ("v5", 5, 1, 0),
+               ("v5 streamed values", 5, 1, 0)]
+    print("value dictionary: %d distinct values" % inf["value_dictionary"])
     print("regular slices %d of %d, index rows %d vs %d" % (
         inf["regular_slices"], inf["nslices"], inf["index_rows"],
         inf["padded_entries"] // 32))
@@ -43,6 +45,7 @@ def main():
     iters = int(os.environ.get("SWEEP_ITERS", "50"))
     for name, variant, ctas, mode in configs:
         capi.set_option("spmv_variant", variant)
+        capi.set_option("value_index", 0 if "streamed" in name else 1)
         capi.set_option("ctas_per_sm", ctas)
         capi.set_option("diag_mode", mode)
         A.spmv_timed(y, x, 3)
