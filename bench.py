@@ -389,9 +389,16 @@ def main():
                           "RED per column and tile)"
                           if info.get("transposed_tiles") else
                           "sym_spmv_reg_kernel<double> (variant 5: compressed "
-                          "index stream, shuffle-merged REDs)",
+                          "index stream, shuffle-merged REDs%s)" % (
+                              ", values dictionary-coded: %d distinct value(s), "
+                              "lossless" % info["value_dictionary"]
+                              if info.get("value_dictionary") else ""),
                 "kernel_ms": kernel_ms_avg,
                 "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "achieved = ALGORITHMIC bytes (SURVEY.md 8d: 12 B per "
+                        "stored entry + vectors) / kernel time; the kernel "
+                        "streams fewer (compressed indices, dictionary-coded "
+                        "values: see traffic), so frac can exceed 1",
                 "hbm_gbs_whole_step": alg_bytes / (ms_per_step * 1e-3) / 1e9,
             },
             "e2e": {

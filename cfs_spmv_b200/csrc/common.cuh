@@ -90,6 +90,7 @@ struct Options {
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int csr_layout = 1; // Format::csr streams the sliced layout (0: warp per row)
   int value_index = 1; // dictionary-coded values where <= 256 distinct (regular matrices)
+  int rechunk = 1;     // ragged matrices: virtual rows of ~1.3 x the mean row length
   int tile6 = 1;      // variant 6 where it applies (bounded column windows)
   int cg_batch = 16; // CG iterations enqueued between two looks at the stop flag
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
@@ -215,7 +216,8 @@ int build_lower(cfs_matrix_s *m, cudaStream_t s);
 int build_layout(cfs_matrix_s *m, cudaStream_t s);
 int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
                       const int32_t *src_colind, const void *src_values,
-                      int64_t src_nnz, cudaStream_t s);
+                      int64_t src_nnz, cudaStream_t s, int chunk = kMaxChunk,
+                      bool rechunk = false);
 // the non-symmetric path, Format::csr (csr_path.cu)
 int tune_csr(cfs_matrix_s *m, int nparts, int tuning, cudaStream_t s);
 int launch_csr_sell(const cfs_matrix_s *m, void *y, const void *x,

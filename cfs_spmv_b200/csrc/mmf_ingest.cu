@@ -195,6 +195,49 @@ HostLine host_parse_line(const char *b, const char *e) {
   return h;
 }
 
+// Temporaries come from the stream-ordered pool (cudaMallocAsync): a buffer
+// released early (the text, the per-line arrays) is handed to a later one (the
+// sort buffers) without another trip to the driver -- cudaMalloc / cudaFree of
+// hundreds of MB each were most of the wall time of an ingest, and its jitter.
+template <typename T> struct PoolArray {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  PoolArray() {}
+  PoolArray(const PoolArray &) = delete;
+  PoolArray &operator=(const PoolArray &) = delete;
+  ~PoolArray() { release(); }
+  int alloc(size_t count, cudaStream_t stream) {
+    release();
+    s = stream;
+    n = count;
+    CFS_CUDA_TRY(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T),
+                                 stream));
+    return CFS_OK;
+  }
+  void release() {
+    if (p)
+      cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+int keep_pool_memory() {
+  static bool done = false;
+  if (done)
+    return CFS_OK;
+  int dev = 0;
+  cudaMemPool_t pool;
+  CFS_CUDA_TRY(cudaGetDevice(&dev));
+  CFS_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+  unsigned long long keep = ~0ULL; // do not hand freed blocks back at every sync
+  CFS_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold,
+                                       &keep));
+  done = true;
+  return CFS_OK;
+}
+
 struct Timer {
   cudaEvent_t e[2] = {nullptr, nullptr};
   cudaStream_t s;
@@ -250,21 +293,22 @@ int ingest(cfs_matrix_s *m, const cfs_mmf_text *in, cfs_mmf_report *rep) {
   cudaStream_t s = m->stream;
   const long long L = in->declared;
   const size_t body = in->bytes - in->entries_offset;
+  CFS_TRY(keep_pool_memory());
   Timer timer(s);
 
   // ---- text -> HBM (only the entry lines)
-  DevArray<char> text;
-  CFS_TRY(text.alloc(body + 1));
+  PoolArray<char> text;
+  CFS_TRY(text.alloc(body + 1, s));
   if (body)
     CFS_CUDA_TRY(cudaMemcpyAsync(text.p, in->text + in->entries_offset, body,
                                  cudaMemcpyHostToDevice, s));
   rep->ms_upload = timer.stop();
 
   // ---- line ends
-  DevArray<int> d_total;
-  CFS_TRY(d_total.alloc(1));
+  PoolArray<int> d_total;
+  CFS_TRY(d_total.alloc(1, s));
   cub::CountingInputIterator<unsigned int> byte_ids(0);
-  DevArray<char> tmp;
+  PoolArray<char> tmp;
   size_t tmp_bytes = 0;
   {
     cub::TransformInputIterator<int, NewlineFlag,
@@ -272,7 +316,7 @@ int ingest(cfs_matrix_s *m, const cfs_mmf_text *in, cfs_mmf_report *rep) {
         flags(byte_ids, NewlineFlag{text.p});
     CFS_CUDA_TRY(cub::DeviceReduce::Sum(nullptr, tmp_bytes, flags, d_total.p,
                                         (long long)body, s));
-    CFS_TRY(tmp.alloc(tmp_bytes));
+    CFS_TRY(tmp.alloc(tmp_bytes, s));
     CFS_CUDA_TRY(cub::DeviceReduce::Sum(tmp.p, tmp_bytes, flags, d_total.p,
                                         (long long)body, s));
   }
@@ -282,29 +326,29 @@ int ingest(cfs_matrix_s *m, const cfs_mmf_text *in, cfs_mmf_report *rep) {
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
   if (total_lines < L) // "Requesting dereference, but mmf ended."
     return needs_host("fewer entry lines than the size line announces");
-  DevArray<unsigned int> nl;
-  CFS_TRY(nl.alloc((size_t)total_lines));
+  PoolArray<unsigned int> nl;
+  CFS_TRY(nl.alloc((size_t)total_lines, s));
   CFS_CUDA_TRY(cub::DeviceSelect::If(nullptr, tmp_bytes, byte_ids, nl.p,
                                      d_total.p, (long long)body,
                                      IsNewline{text.p}, s));
-  CFS_TRY(tmp.alloc(tmp_bytes));
+  CFS_TRY(tmp.alloc(tmp_bytes, s));
   CFS_CUDA_TRY(cub::DeviceSelect::If(tmp.p, tmp_bytes, byte_ids, nl.p,
                                      d_total.p, (long long)body,
                                      IsNewline{text.p}, s));
 
   // ---- one thread per line
-  DevArray<int> row, col, count;
-  DevArray<double> val;
-  CFS_TRY(row.alloc((size_t)L));
-  CFS_TRY(col.alloc((size_t)L));
-  CFS_TRY(count.alloc((size_t)L));
-  CFS_TRY(val.alloc((size_t)L));
+  PoolArray<int> row, col, count;
+  PoolArray<double> val;
+  CFS_TRY(row.alloc((size_t)L, s));
+  CFS_TRY(col.alloc((size_t)L, s));
+  CFS_TRY(count.alloc((size_t)L, s));
+  CFS_TRY(val.alloc((size_t)L, s));
   const unsigned int host_capacity = (unsigned int)L;
-  DevArray<unsigned int> host_list, host_count;
-  DevArray<unsigned long long> first_error;
-  CFS_TRY(host_list.alloc((size_t)L));
-  CFS_TRY(host_count.alloc(1));
-  CFS_TRY(first_error.alloc(1));
+  PoolArray<unsigned int> host_list, host_count;
+  PoolArray<unsigned long long> first_error;
+  CFS_TRY(host_list.alloc((size_t)L, s));
+  CFS_TRY(host_count.alloc(1, s));
+  CFS_TRY(first_error.alloc(1, s));
   CFS_CUDA_TRY(cudaMemsetAsync(host_count.p, 0, 4, s));
   CFS_CUDA_TRY(cudaMemsetAsync(first_error.p, 0xff, 8, s));
   const int mirror = in->file_symmetric ? 1 : 0;
@@ -353,11 +397,11 @@ int ingest(cfs_matrix_s *m, const cfs_mmf_text *in, cfs_mmf_report *rep) {
       pcol[k] = c;
       pval[k] = h.val;
     }
-    DevArray<int> d_prow, d_pcol;
-    DevArray<double> d_pval;
-    CFS_TRY(d_prow.alloc(nhost));
-    CFS_TRY(d_pcol.alloc(nhost));
-    CFS_TRY(d_pval.alloc(nhost));
+    PoolArray<int> d_prow, d_pcol;
+    PoolArray<double> d_pval;
+    CFS_TRY(d_prow.alloc(nhost, s));
+    CFS_TRY(d_pcol.alloc(nhost, s));
+    CFS_TRY(d_pval.alloc(nhost, s));
     CFS_CUDA_TRY(cudaMemcpyAsync(d_prow.p, prow.data(), (size_t)nhost * 4,
                                  cudaMemcpyHostToDevice, s));
     CFS_CUDA_TRY(cudaMemcpyAsync(d_pcol.p, pcol.data(), (size_t)nhost * 4,
@@ -377,12 +421,12 @@ int ingest(cfs_matrix_s *m, const cfs_mmf_text *in, cfs_mmf_report *rep) {
 
   // ---- mirror the off-diagonal entries of a symmetric file
   long long nnz = L;
-  DevArray<long long> offset;
+  PoolArray<long long> offset;
   if (mirror && L) {
-    CFS_TRY(offset.alloc((size_t)L));
+    CFS_TRY(offset.alloc((size_t)L, s));
     CFS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, count.p,
                                                offset.p, L, s));
-    CFS_TRY(tmp.alloc(tmp_bytes));
+    CFS_TRY(tmp.alloc(tmp_bytes, s));
     CFS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, count.p,
                                                offset.p, L, s));
     long long last_off = 0;
@@ -396,12 +440,12 @@ int ingest(cfs_matrix_s *m, const cfs_mmf_text *in, cfs_mmf_report *rep) {
   }
   if (nnz > 0x7fffffffLL)
     return needs_host("more entries than a 32-bit index holds");
-  DevArray<unsigned long long> key, key_alt;
-  DevArray<double> xval, xval_alt;
-  CFS_TRY(key.alloc((size_t)nnz));
-  CFS_TRY(key_alt.alloc((size_t)nnz));
-  CFS_TRY(xval.alloc((size_t)nnz));
-  CFS_TRY(xval_alt.alloc((size_t)nnz));
+  PoolArray<unsigned long long> key, key_alt;
+  PoolArray<double> xval, xval_alt;
+  CFS_TRY(key.alloc((size_t)nnz, s));
+  CFS_TRY(key_alt.alloc((size_t)nnz, s));
+  CFS_TRY(xval.alloc((size_t)nnz, s));
+  CFS_TRY(xval_alt.alloc((size_t)nnz, s));
   if (L)
     expand_kernel<<<grid, kThreads, 0, s>>>(L, row.p, col.p, val.p, count.p,
                                             mirror ? offset.p : nullptr, key.p,
@@ -421,7 +465,7 @@ int ingest(cfs_matrix_s *m, const cfs_mmf_text *in, cfs_mmf_report *rep) {
   cub::DoubleBuffer<double> vals(xval.p, xval_alt.p);
   CFS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, vals,
                                                nnz, 0, 32 + row_bits, s));
-  CFS_TRY(tmp.alloc(tmp_bytes));
+  CFS_TRY(tmp.alloc(tmp_bytes, s));
   if (nnz)
     CFS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys, vals,
                                                  nnz, 0, 32 + row_bits, s));
@@ -484,6 +528,14 @@ int cfs_cuda_matrix_create_from_mmf(cfs_mat_t *out, const cfs_mmf_text *in,
                        __LINE__);
   if (status == CFS_OK)
     status = ingest(m, in, report);
+  { // hand the pool's blocks back: tune() allocates with cudaMalloc
+    cudaMemPool_t pool;
+    if (m->stream)
+      cudaStreamSynchronize(m->stream);
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+      cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+  }
   if (status != CFS_OK) {
     cfs_cuda_matrix_destroy(m);
     return status;

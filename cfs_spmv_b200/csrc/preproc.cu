@@ -86,17 +86,17 @@ __global__ void fill_lower_kernel(int nrows, int row_begin,
 }
 
 // ---- virtual rows ----------------------------------------------------------
-__global__ void count_vrows_kernel(int nrows,
+__global__ void count_vrows_kernel(int nrows, int chunk,
                                    const int *__restrict__ low_rowptr,
                                    int *__restrict__ nv) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows)
     return;
   const int len = low_rowptr[i + 1] - low_rowptr[i];
-  nv[i] = len == 0 ? 1 : (len + kMaxChunk - 1) / kMaxChunk;
+  nv[i] = len == 0 ? 1 : (len + chunk - 1) / chunk;
 }
 
-__global__ void fill_vrows_kernel(int nrows, int row_begin,
+__global__ void fill_vrows_kernel(int nrows, int row_begin, int max_chunk,
                                   const int *__restrict__ low_rowptr,
                                   const int *__restrict__ voff,
                                   int *__restrict__ vrow_row,
@@ -110,7 +110,7 @@ __global__ void fill_vrows_kernel(int nrows, int row_begin,
   int v = voff[i];
   int done = 0, chunk = 0;
   do {
-    const int take = min(kMaxChunk, len - done);
+    const int take = min(max_chunk, len - done);
     vrow_row[v] = (row_begin + i) | (chunk ? kVrowCont : 0);
     vrow_start[v] = begin + done;
     vrow_len[v] = take;
@@ -118,6 +118,23 @@ __global__ void fill_vrows_kernel(int nrows, int row_begin,
     ++v;
     ++chunk;
   } while (done < len);
+}
+
+// largest distance between a row and its first stored column (the CSR the
+// layout is cut from keeps the columns of a row ascending)
+__global__ void bandwidth_kernel(int nrows, int row_begin,
+                                 const int *__restrict__ rowptr,
+                                 const int *__restrict__ colind,
+                                 int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int d = 0;
+  if (i < nrows && rowptr[i + 1] > rowptr[i])
+    d = max(0, row_begin + i - colind[rowptr[i]]);
+  typedef cub::BlockReduce<int, kThreads> Reduce;
+  __shared__ typename Reduce::TempStorage tmp;
+  d = Reduce(tmp).Reduce(d, cub::Max());
+  if (threadIdx.x == 0)
+    atomicMax(out, d);
 }
 
 __global__ void slice_width_kernel(long long nvrows, long long nslices,
@@ -320,14 +337,19 @@ int build_lower(cfs_matrix_s *m, cudaStream_t s) {
 
 int build_layout(cfs_matrix_s *m, cudaStream_t s) {
   return build_layout_from(m, m->low_rowptr.p, m->low_colind.p,
-                           m->low_values.p, m->nnz_low, s);
+                           m->low_values.p, m->nnz_low, s, kMaxChunk, true);
 }
 
 // rowptr / colind / values: the CSR the layout is cut from -- the lower
 // triangle for a symmetric matrix, the full CSR for Format::csr (csr_path.cu)
+// chunk: longest virtual row. rechunk: a ragged matrix (its natural order pads
+// too much) may restart with shorter chunks, about 1.3 x the mean row length:
+// after length-sorting the slices of a row block are then nearly equally long,
+// which is what the tile kernel (one warp per slice, a barrier per tile) needs.
 int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
                       const int32_t *src_colind, const void *src_values,
-                      int64_t src_nnz, cudaStream_t s) {
+                      int64_t src_nnz, cudaStream_t s, int chunk,
+                      bool rechunk) {
   const int n = m->nrows;
   // virtual rows
   DevArray<int> nv, voff;
@@ -335,8 +357,8 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
   CFS_TRY(voff.alloc((size_t)n + 1));
   CFS_CUDA_TRY(cudaMemsetAsync(nv.p, 0, ((size_t)n + 1) * 4, s));
   if (n > 0)
-    count_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(n, src_rowptr,
-                                                          nv.p);
+    count_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(n, chunk,
+                                                          src_rowptr, nv.p);
   CFS_CUDA_TRY(cudaGetLastError());
   CFS_TRY(exclusive_scan_i32(nv.p, voff.p, (size_t)n + 1, s));
   int nvrows = 0;
@@ -350,7 +372,7 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
   CFS_TRY(vlen.alloc(nlanes));
   if (n > 0)
     fill_vrows_kernel<<<blocks_for(n), kThreads, 0, s>>>(
-        n, m->row_begin, src_rowptr, voff.p, m->vrow_row.p, vstart.p,
+        n, m->row_begin, chunk, src_rowptr, voff.p, m->vrow_row.p, vstart.p,
         vlen.p);
   CFS_CUDA_TRY(cudaGetLastError());
   // slice widths -> slice_ptr; if the natural order pads too much, sort the
@@ -377,6 +399,27 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
     const double limit = attempt == 0 ? 1.15 : 1.5;
     if (padding <= limit || attempt == 2 || g_options.sort_rows == 0)
       break;
+    if (attempt == 0 && rechunk && chunk == kMaxChunk && n > 0 &&
+        g_options.rechunk && g_options.tile6) {
+      // only where the tile kernel will run: the column window of a row block
+      // (its rows + the bandwidth) has to fit (tiles6.cu); a power-law matrix
+      // keeps the long chunks (R-MAT scale 24: 1.01 ms vs 1.33 ms re-chunked)
+      DevArray<int> bw;
+      CFS_TRY(bw.alloc(1));
+      CFS_CUDA_TRY(cudaMemsetAsync(bw.p, 0, 4, s));
+      bandwidth_kernel<<<blocks_for(n), kThreads, 0, s>>>(
+          n, m->row_begin, src_rowptr, src_colind, bw.p);
+      CFS_CUDA_TRY(cudaGetLastError());
+      int bandwidth = 0;
+      CFS_CUDA_TRY(cudaMemcpy(&bandwidth, bw.p, 4, cudaMemcpyDeviceToHost));
+      const double mean = (double)src_nnz / (double)n;
+      int shorter = (int)(1.3 * mean + 0.999);
+      shorter = shorter < 8 ? 8 : shorter;
+      if (shorter < kMaxChunk &&
+          bandwidth + 2 * kT6Slices * kSliceRows < kT6MaxCols)
+        return build_layout_from(m, src_rowptr, src_colind, src_values,
+                                 src_nnz, s, shorter, false);
+    }
     // first try: sort inside the row blocks that become the tiles of variant 6
     const long long window =
         attempt == 0 ? kT6Slices * kSliceRows : (long long)1 << 30;

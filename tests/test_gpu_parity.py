@@ -138,9 +138,17 @@ def test_long_rows_are_split(gpu):
     ci, v = cols[order].astype(np.int32), vals[order]
     x = gen.gen_x(5, n)
     for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        capi.set_option("rechunk", 0)
         A = capi.Matrix.from_csr(rp, ci, v.astype(dt))
         A.tune(1)
+        capi.set_option("rechunk", 1)
         assert A.info()["nvrows"] == (n - 1) + 32  # ceil(999/32) chunks
+        A.close()
+        # ragged + small bandwidth: shorter chunks (8 = the minimum) for the
+        # tile kernel
+        A = capi.Matrix.from_csr(rp, ci, v.astype(dt))
+        A.tune(1)
+        assert A.info()["nvrows"] == (n - 1) + 125  # ceil(999/8) chunks
         y = np.zeros(n, dt)
         A.spmv(y, x.astype(dt))
         o = oracle.Oracle(rp, ci, v.astype(dt), 1)
