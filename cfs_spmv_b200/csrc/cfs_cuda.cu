@@ -94,6 +94,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.value_index = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "rechunk_pct") && value >= 100 && value <= 400) {
+    g_options.rechunk_pct = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "rechunk") && (value == 0 || value == 1)) {
     g_options.rechunk = (int)value;
     return CFS_OK;

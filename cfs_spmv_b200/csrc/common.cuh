@@ -90,6 +90,7 @@ struct Options {
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int csr_layout = 1; // Format::csr streams the sliced layout (0: warp per row)
   int value_index = 1; // dictionary-coded values where <= 256 distinct (regular matrices)
+  int rechunk_pct = 130; // ... as a percentage of the mean row length
   int rechunk = 1;     // ragged matrices: virtual rows of ~1.3 x the mean row length
   int tile6 = 1;      // variant 6 where it applies (bounded column windows)
   int cg_batch = 16; // CG iterations enqueued between two looks at the stop flag

@@ -413,7 +413,7 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
       int bandwidth = 0;
       CFS_CUDA_TRY(cudaMemcpy(&bandwidth, bw.p, 4, cudaMemcpyDeviceToHost));
       const double mean = (double)src_nnz / (double)n;
-      int shorter = (int)(1.3 * mean + 0.999);
+      int shorter = (int)(g_options.rechunk_pct * 0.01 * mean + 0.999);
       shorter = shorter < 8 ? 8 : shorter;
       if (shorter < kMaxChunk &&
           bandwidth + 2 * kT6Slices * kSliceRows < kT6MaxCols)
