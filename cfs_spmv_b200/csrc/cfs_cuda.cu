@@ -32,13 +32,15 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 static int g_device = -1;
 Options g_options;
 
-static int require_device() {
+int require_device() {
   if (g_device >= 0) {
     CFS_CUDA_TRY(cudaSetDevice(g_device));
     return CFS_OK;
   }
   return cfs_cuda_init(0);
 }
+
+int current_device() { return g_device; }
 
 enum PtrKind { kPtrHost, kPtrDevice };
 

@@ -13,6 +13,10 @@ namespace cfsb {
 
 // ---- error plumbing ------------------------------------------------------
 void set_error(const char *fmt, ...);
+// binds the process to its device on first use (cfs_cuda_init(0) by default);
+// CFS_ERR_NO_DEVICE without an sm_100 GPU -- there is no CPU fallback
+int require_device();
+int current_device();
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 #define CFS_CUDA_TRY(call)                                                     \

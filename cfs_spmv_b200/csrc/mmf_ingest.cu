@@ -506,12 +506,8 @@ int cfs_cuda_matrix_create_from_mmf(cfs_mat_t *out, const cfs_mmf_text *in,
   memset(report, 0, sizeof(*report));
   if (in->bytes - in->entries_offset >= 0xffffffffULL)
     return needs_host("file image of 4 GiB or more");
-  int device = 0;
-  {
-    const cudaError_t e = cudaGetDevice(&device);
-    if (e != cudaSuccess)
-      return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
-  }
+  CFS_TRY(require_device());
+  const int device = current_device();
   cfs_matrix_s *m = new cfs_matrix_s;
   m->device = device;
   m->is_double = is_double != 0;

@@ -109,6 +109,30 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
         b"CUDA" in capi.lib().cfs_cuda_last_error()
 
 
+def test_ingest_and_solver_fail_loudly_without_a_gpu(tmp_path):
+    """the entry points next to the path have no CPU fallback either; only the
+    header scan (host code, like the reference's loader) works anywhere"""
+    path = str(tmp_path / "m.mtx")
+    open(path, "w").write("%%MatrixMarket matrix coordinate real symmetric\n"
+                          "% comment\n3 3 2\n1 1 2.0\n2 1 1.0\n")
+    image = np.fromfile(path, dtype=np.uint8)
+    h = capi.HostMmfHeader()
+    assert capi.host_lib().cfs_host_scan_mmf_header(
+        image.ctypes.data, image.size, ctypes.byref(h)) == 0
+    assert (h.nrows, h.ncols, h.declared, h.symmetric, h.zero_based) == \
+        (3, 3, 2, 1, 0)
+    assert bytes(image[h.entries_offset:h.entries_offset + 3]) == b"1 1"
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.CfsError) as e:
+        capi.Matrix.from_mmf(path)
+    assert e.value.code == capi.CFS_ERR_NO_DEVICE
+    res = capi.CgResult()
+    assert capi.lib().cfs_cuda_cg_solve(None, None, None, 1, 1e-6,
+                                        ctypes.byref(res), None, 0) == \
+        capi.CFS_ERR_INVALID
+
+
 def test_host_alloc_is_64_byte_aligned_and_freeable():
     L = capi.lib()
     for nbytes in (1, 64, 4096, 1 << 20):
