@@ -71,7 +71,15 @@ __global__ void __launch_bounds__(kThreads)
   code[i] = c;
 }
 
-// the real entries' bit patterns, compacted, for sort + unique
+__global__ void __launch_bounds__(kThreads)
+    first_real_kernel(long long n, const int *__restrict__ col,
+                      unsigned long long *__restrict__ first) {
+  const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (i < n && col[i] >= 0)
+    atomicMin(first, (unsigned long long)i);
+}
+
+// the real entries' bit patterns (padding replaced), for sort + unique
 template <typename U>
 __global__ void __launch_bounds__(kThreads)
     gather_bits_kernel(long long n, long long stride, long long count,
@@ -127,26 +135,23 @@ template <typename T> int build_typed(cfs_matrix_s *m, cudaStream_t s) {
   const long long n = m->padded_entries;
   const U *val = (const U *)m->sell_val.p;
   const int *col = m->sell_col.p;
-  // a value that is certainly in the matrix, to stand in for padding / holes
+  // a value that is certainly in the matrix stands in for padding in the
+  // sort: the first real entry
   U filler = 0;
   {
-    // first real entry: slice-column-major, so look at the first slice's rows
-    std::vector<int> c(kSliceRows);
-    std::vector<U> v(kSliceRows);
-    bool found = false;
-    for (long long base = 0; base < n && !found; base += (long long)kSliceRows << 10) {
-      CFS_CUDA_TRY(cudaMemcpy(c.data(), col + base, kSliceRows * 4,
-                              cudaMemcpyDeviceToHost));
-      CFS_CUDA_TRY(cudaMemcpy(v.data(), val + base, kSliceRows * sizeof(U),
-                              cudaMemcpyDeviceToHost));
-      for (int k = 0; k < kSliceRows && !found; ++k)
-        if (c[k] >= 0) {
-          filler = v[k];
-          found = true;
-        }
-    }
-    if (!found)
-      return CFS_OK; // no entry found where we looked: leave the values alone
+    DevArray<unsigned long long> first;
+    CFS_TRY(first.alloc(1));
+    CFS_CUDA_TRY(cudaMemsetAsync(first.p, 0xff, 8, s));
+    first_real_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0,
+                        s>>>(n, col, first.p);
+    CFS_CUDA_TRY(cudaGetLastError());
+    unsigned long long at = 0;
+    CFS_CUDA_TRY(cudaMemcpyAsync(&at, first.p, 8, cudaMemcpyDeviceToHost, s));
+    CFS_CUDA_TRY(cudaStreamSynchronize(s));
+    if (at == ~0ULL)
+      return CFS_OK; // no stored lower entry at all
+    CFS_CUDA_TRY(cudaMemcpy(&filler, val + at, sizeof(U),
+                            cudaMemcpyDeviceToHost));
   }
   CFS_TRY(m->vcode.alloc((size_t)n));
   DevArray<U> dict;

@@ -211,3 +211,25 @@ def test_gpu_ingest_large_file_and_spmv(gpu, tmp_path):
                         shape=(n, n)) @ x
     assert np.linalg.norm(y - ref) <= 1e-12 * np.linalg.norm(ref)
     A.close()
+
+
+def test_gpu_ingest_degenerate_files(gpu, tmp_path):
+    """no entries at all, diagonal only, CR LF line ends, 1 x 1"""
+    banner = "%%MatrixMarket matrix coordinate real symmetric\n"
+    files = {
+        "empty.mtx": banner + "4 4 0\n",
+        "diag.mtx": banner + "3 3 3\n1 1 1.5\n2 2 2.5\n3 3 3.5\n",
+        "crlf.mtx": banner + "3 3 3\r\n1 1 1.5\r\n2 1 -2.5\r\n3 3 3.5\r\n",
+        "one.mtx": banner + "1 1 1\n1 1 7\n",
+    }
+    for name, text in files.items():
+        p = str(tmp_path / name)
+        open(p, "w", newline="").write(text)
+        same_csr(load_with(p, True), load_with(p, False))
+        A, h, rep = capi.Matrix.from_mmf(p)   # the GPU path took it
+        A.close()
+    A, h, rep = capi.Matrix.from_mmf(str(tmp_path / "empty.mtx"))
+    assert rep["nnz"] == 0
+    rp, ci, v = A.download_csr(4, 0)
+    assert not rp.any()
+    A.close()
