@@ -406,8 +406,9 @@ def main():
                 "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                 "path": "cfs_cuda_spmv(host y, host x): pinned H2D, kernel and D2H "
-                        "overlapped in 8 row chunks, the step replayed as one "
-                        "CUDA graph"
+                        "overlapped in 6 row chunks (each run as head + rest so "
+                        "that y of the previous chunk can leave early), the step "
+                        "replayed as one CUDA graph"
                         if world == 1 else
                         "pinned H2D of x shard+halo, kernel, NCCL y halo, D2H",
             },

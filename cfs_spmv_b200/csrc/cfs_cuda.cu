@@ -128,8 +128,8 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.pipeline = (int)value;
     return CFS_OK;
   }
-  if (!strcmp(key, "pipeline_ramp") && (value == 0 || value == 1)) {
-    g_options.pipeline_ramp = (int)value;
+  if (!strcmp(key, "pipeline_split") && (value == 0 || value == 1)) {
+    g_options.pipeline_split = (int)value;
     return CFS_OK;
   }
   if (!strcmp(key, "pipeline_smem") && value >= 0 && value <= 200 * 1024) {
@@ -569,42 +569,38 @@ int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
 // 162-167, calls with the same two vectors every time).
 static int enqueue_pipeline(cfs_mat_t m, void *y, const void *x, bool fork) {
   const size_t vs = m->vsize();
-  const size_t K = m->chunks.size();
+  const size_t S = m->stages.size();
   char *xd = m->stage_x.p, *yd = m->stage_y.p;
+  const bool trace = g_options.pipeline_trace && !fork;
   if (fork) { // bring the copy streams into the capture
     CFS_CUDA_TRY(cudaEventRecord(m->ev_fork, m->stream));
     CFS_CUDA_TRY(cudaStreamWaitEvent(m->h2d_stream, m->ev_fork, 0));
   }
-  if (g_options.pipeline_trace && !fork)
+  if (trace)
     CFS_CUDA_TRY(cudaEventRecord(m->ev_fork, m->stream));
   CFS_CUDA_TRY(cudaMemsetAsync(yd, 0, (size_t)m->nrows * vs, m->stream));
-  size_t next_out = 0;
-  for (size_t c = 0; c < K; ++c) {
-    const cfs_matrix_s::Chunk &ch = m->chunks[c];
-    const size_t xo = (size_t)ch.row0 * vs;
-    // the last chunk also carries the columns beyond the last row (none for a
-    // square matrix, kept for safety)
-    const size_t xe = (c + 1 == K ? (size_t)m->ncols : (size_t)ch.row1) * vs;
+  for (size_t j = 0; j < S; ++j) {
+    const cfs_matrix_s::Stage &st = m->stages[j];
+    const size_t xo = (size_t)st.x_row0 * vs, xe = (size_t)st.x_row1 * vs;
     if (xe > xo && !(g_options.pipeline_skip & 4))
       CFS_CUDA_TRY(cudaMemcpyAsync(xd + xo, (const char *)x + xo, xe - xo,
                                    cudaMemcpyHostToDevice, m->h2d_stream));
-    CFS_CUDA_TRY(cudaEventRecord(m->ev_x[c], m->h2d_stream));
-    CFS_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_x[c], 0));
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_x[j], m->h2d_stream));
+    CFS_CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_x[j], 0));
     if (!(g_options.pipeline_skip & 1))
       CFS_TRY(launch_sym_spmv(m, yd, xd, m->stream, nullptr, nullptr, nullptr,
-                              true, ch.slice0, ch.slice1));
-    CFS_CUDA_TRY(cudaEventRecord(m->ev_k[c], m->stream));
-    while (next_out < K && m->chunks[next_out].final_after <= (int)c) {
-      const cfs_matrix_s::Chunk &o = m->chunks[next_out];
-      const size_t yo = (size_t)o.row0 * vs, ye = (size_t)o.row1 * vs;
-      CFS_CUDA_TRY(cudaStreamWaitEvent(m->d2h_stream, m->ev_k[c], 0));
+                              true, st.slice0, st.slice1));
+    CFS_CUDA_TRY(cudaEventRecord(m->ev_k[j], m->stream));
+    if (!st.y_ready.empty())
+      CFS_CUDA_TRY(cudaStreamWaitEvent(m->d2h_stream, m->ev_k[j], 0));
+    for (const std::pair<int, int> &r : st.y_ready) {
+      const size_t yo = (size_t)r.first * vs, ye = (size_t)r.second * vs;
       if (ye > yo && !(g_options.pipeline_skip & 2))
         CFS_CUDA_TRY(cudaMemcpyAsync((char *)y + yo, yd + yo, ye - yo,
                                      cudaMemcpyDeviceToHost, m->d2h_stream));
-      if (g_options.pipeline_trace && !fork)
-        CFS_CUDA_TRY(cudaEventRecord(m->ev_d[next_out], m->d2h_stream));
-      ++next_out;
     }
+    if (trace)
+      CFS_CUDA_TRY(cudaEventRecord(m->ev_d[j], m->d2h_stream));
   }
   if (fork) { // join: the capture ends on m->stream
     CFS_CUDA_TRY(cudaEventRecord(m->ev_join, m->d2h_stream));
@@ -616,7 +612,7 @@ static int enqueue_pipeline(cfs_mat_t m, void *y, const void *x, bool fork) {
 static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x,
                                bool pinned) {
   const size_t vs = m->vsize();
-  const size_t K = m->chunks.size();
+  const size_t K = m->stages.size();
   if (!m->h2d_stream) {
     CFS_CUDA_TRY(cudaStreamCreateWithFlags(&m->h2d_stream,
                                            cudaStreamNonBlocking));
@@ -675,9 +671,10 @@ static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x,
       cudaEventElapsedTime(&tx, m->ev_fork, m->ev_x[c]);
       cudaEventElapsedTime(&tk, m->ev_fork, m->ev_k[c]);
       cudaEventElapsedTime(&td, m->ev_fork, m->ev_d[c]);
-      printf("pipeline chunk %2zu: x in %.3f ms, kernel done %.3f, y out %.3f "
-             "(final after chunk %d)\n", c, tx, tk, td,
-             m->chunks[c].final_after);
+      printf("pipeline stage %2zu (slices %lld..%lld): x rows %d..%d in at "
+             "%.3f ms, kernel done %.3f, %zu y range(s) out by %.3f\n", c,
+             m->stages[c].slice0, m->stages[c].slice1, m->stages[c].x_row0,
+             m->stages[c].x_row1, tx, tk, m->stages[c].y_ready.size(), td);
     }
     fflush(stdout);
   }
@@ -701,7 +698,7 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   bool px = false, py = false;
   classify(x, &kx, &px);
   classify(y, &ky, &py);
-  if (kx == kPtrHost && ky == kPtrHost && m->symmetric && !m->chunks.empty() &&
+  if (kx == kPtrHost && ky == kPtrHost && m->symmetric && !m->stages.empty() &&
       g_options.pipeline)
     return spmv_host_pipelined(m, y, x, px && py);
   const void *xd = x;

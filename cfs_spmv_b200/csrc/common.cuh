@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "cfs_cuda.h"
@@ -87,10 +88,10 @@ struct Options {
   int pipeline = 1;  // overlap H2D / kernel / D2H in cfs_cuda_spmv(host, host)
   int pipeline_trace = 0;   // print the per-chunk timeline (development aid)
   int pipeline_graph = 1;   // replay the pipelined step as one CUDA graph
-  int pipeline_chunks = 8;  // row chunks of the pipeline (read at tune time)
+  int pipeline_chunks = 6;  // row chunks of the pipeline (read at tune time)
   int pipeline_skip = 0;    // measurement aid: 1 no kernels, 2 no D2H, 4 no H2D
   int pipeline_smem = 0;    // dynamic smem of pipelined launches (occupancy cap)
-  int pipeline_ramp = 0;    // graded chunk sizes instead of equal ones (slower)
+  int pipeline_split = 1;   // chunks run as head + rest (see build_pipeline_plan)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time
   int csr_layout = 1; // Format::csr streams the sliced layout (0: warp per row)
   int value_index = 1; // dictionary-coded values where <= 256 distinct (regular matrices)
@@ -200,12 +201,15 @@ struct cfs_matrix_s {
   // only looks DOWN, so a chunk of rows can run as soon as x up to its last row
   // has arrived, and its y rows are final once every chunk that reaches down
   // into them is done: H2D, kernel and D2H overlap chunk by chunk.
-  struct Chunk {
+  // A stage = a range of slices (a whole chunk, or its head / its rest, see
+  // build_pipeline_plan): the x rows it needs beyond the earlier stages and
+  // the y row ranges that are final once it has run.
+  struct Stage {
     long long slice0, slice1;
-    int row0, row1;       // rows whose y this chunk owns
-    int final_after;      // index of the last chunk that adds into these rows
+    int x_row0, x_row1;
+    std::vector<std::pair<int, int>> y_ready;
   };
-  std::vector<Chunk> chunks;
+  std::vector<Stage> stages;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> ev_x, ev_k, ev_d;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

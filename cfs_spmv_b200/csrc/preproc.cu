@@ -498,91 +498,137 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
 }
 
 namespace {
-// min column of the entries of slices [slice0, slice1)
-__global__ void chunk_min_col_kernel(const int *__restrict__ slice_ptr,
-                                     const int *__restrict__ sell_col,
-                                     long long slice0, long long slice1,
-                                     int *__restrict__ out) {
-  const size_t begin = (size_t)slice_ptr[slice0] * kSliceRows;
-  const size_t end = (size_t)slice_ptr[slice1] * kSliceRows;
-  int lo = INT_MAX;
-  for (size_t i = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-       i < end; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = sell_col[i];
+// per slice: smallest column it touches (INT_MAX: none), the row tag of its
+// first lane and the largest row it holds
+__global__ void slice_reach_kernel(long long nslices,
+                                   const int *__restrict__ slice_ptr,
+                                   const int *__restrict__ vrow_row,
+                                   const int *__restrict__ sell_col,
+                                   int *__restrict__ min_col,
+                                   int *__restrict__ first_tag,
+                                   int *__restrict__ max_row) {
+  const long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  const int p0 = slice_ptr[s], w = slice_ptr[s + 1] - p0;
+  const int tag = vrow_row[s * kSliceRows + lane];
+  int lo = INT_MAX, hi = tag >= 0 ? (tag & kVrowRowMask) : -1;
+  const int *cp = sell_col + (size_t)p0 * kSliceRows + lane;
+  for (int k = 0; k < w; ++k) {
+    const int c = cp[(size_t)k * kSliceRows];
     if (c >= 0)
       lo = min(lo, c);
   }
-  typedef cub::BlockReduce<int, kThreads> Reduce;
-  __shared__ typename Reduce::TempStorage tmp;
-  lo = Reduce(tmp).Reduce(lo, cub::Min());
-  if (threadIdx.x == 0)
-    atomicMin(out, lo);
+  for (int o = 16; o; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) {
+    min_col[s] = lo;
+    first_tag[s] = tag;
+    max_row[s] = hi;
+  }
 }
 } // namespace
 
-// Chunks of consecutive slices for the host-vector pipeline of cfs_cuda_spmv.
+// Stages of the host-vector pipeline of cfs_cuda_spmv (see cfs_matrix_s::Stage).
 // Only for layouts in natural row order on an unsharded matrix.
+//
+// The slices are cut into pipeline_chunks equal chunks. The y rows of chunk c-1
+// are final once every slice that reaches below the first row of chunk c has
+// run -- in a banded / stencil matrix those are the FIRST few slices of chunk c
+// (its "head": 40 k of 1 M rows for the 27-point Laplacian). So chunk c runs as
+// two stages, head and rest: after the head (which needs only the head's rows
+// of x) the D2H of chunk c-1 starts, while the H2D of the rest of chunk c is
+// still under way. Without the split y lags x by a whole chunk in each
+// direction (tools/e2e_probe.py).
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
-  m->chunks.clear();
+  m->stages.clear();
   if (m->sharded || m->sort_window != 0 || m->nslices < 4096)
     return CFS_OK;
-  // pipeline_chunks equal chunks (8: every chunk costs ~10 us of cross-stream
-  // hand-over, tools/e2e_probe.py). pipeline_ramp = 1 grades the sizes (small
-  // first H2D / last D2H); measured slower on B200, kept as an experiment.
-  std::vector<int> weight;
-  if (g_options.pipeline_ramp)
-    weight = {1, 1, 2, 4, 8, 8, 4, 2, 1, 1};
-  else
-    weight.assign((size_t)g_options.pipeline_chunks, 1);
-  const int K = (int)weight.size();
-  long long total = 0;
-  for (int w : weight)
-    total += w;
-  std::vector<long long> cut(K + 1, 0);
-  long long acc = 0;
-  for (int c = 0; c < K; ++c) {
-    acc += weight[c];
-    cut[c + 1] = m->nslices * acc / total;
-  }
-  // first row of each chunk = row tag of its first lane
-  std::vector<int> row0(K + 1, m->nrows);
-  for (int c = 0; c < K; ++c) {
-    int tag = 0;
-    CFS_CUDA_TRY(cudaMemcpy(&tag, m->vrow_row.p + cut[c] * kSliceRows, 4,
-                            cudaMemcpyDeviceToHost));
-    if (tag < 0)
-      return CFS_OK;
-    row0[c] = tag & kVrowRowMask;
-  }
-  DevArray<int> lo_dev;
-  CFS_TRY(lo_dev.alloc(K));
-  std::vector<int> init(K, INT_MAX), lo(K);
-  CFS_CUDA_TRY(cudaMemcpyAsync(lo_dev.p, init.data(), K * 4,
-                               cudaMemcpyHostToDevice, s));
-  for (int c = 0; c < K; ++c)
-    chunk_min_col_kernel<<<256, kThreads, 0, s>>>(m->slice_ptr.p, m->sell_col.p,
-                                                 cut[c], cut[c + 1],
-                                                 lo_dev.p + c);
+  const long long ns = m->nslices;
+  DevArray<int> d_min, d_tag, d_max;
+  CFS_TRY(d_min.alloc((size_t)ns));
+  CFS_TRY(d_tag.alloc((size_t)ns));
+  CFS_TRY(d_max.alloc((size_t)ns));
+  slice_reach_kernel<<<blocks_for((size_t)ns * 32), kThreads, 0, s>>>(
+      ns, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p, d_min.p, d_tag.p,
+      d_max.p);
   CFS_CUDA_TRY(cudaGetLastError());
-  CFS_CUDA_TRY(cudaMemcpyAsync(lo.data(), lo_dev.p, K * 4,
+  std::vector<int> min_col((size_t)ns), tag((size_t)ns), max_row((size_t)ns);
+  CFS_CUDA_TRY(cudaMemcpyAsync(min_col.data(), d_min.p, (size_t)ns * 4,
+                               cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaMemcpyAsync(tag.data(), d_tag.p, (size_t)ns * 4,
+                               cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaMemcpyAsync(max_row.data(), d_max.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  // natural row order: first rows of the slices ascend, every slice starts
+  // with a live lane
+  for (long long i = 0; i < ns; ++i)
+    if (tag[i] < 0 || (i > 0 && (tag[i] & kVrowRowMask) <
+                                    (tag[i - 1] & kVrowRowMask)))
+      return CFS_OK;
+  const int K = g_options.pipeline_chunks;
+  std::vector<long long> cut((size_t)K + 1);
+  for (int c = 0; c <= K; ++c)
+    cut[c] = ns * c / K;
+  // stage boundaries: chunk starts, and inside chunk c (c >= 1) the end of its
+  // head = one past the last slice that reaches below the chunk's first row
+  std::vector<long long> bound;
+  std::vector<int> chunk_first_stage((size_t)K + 1, 0);
   for (int c = 0; c < K; ++c) {
-    if (row0[c + 1] < row0[c])
-      return CFS_OK; // not in row order after all
-    cfs_matrix_s::Chunk ch;
-    ch.slice0 = cut[c];
-    ch.slice1 = cut[c + 1];
-    ch.row0 = row0[c];
-    ch.row1 = row0[c + 1];
-    ch.final_after = c;
-    m->chunks.push_back(ch);
+    chunk_first_stage[c] = (int)bound.size();
+    bound.push_back(cut[c]);
+    if (c == 0 || !g_options.pipeline_split)
+      continue;
+    const int first_row = tag[cut[c]] & kVrowRowMask;
+    long long head_end = cut[c];
+    for (long long i = cut[c]; i < cut[c + 1]; ++i)
+      if (min_col[i] < first_row)
+        head_end = i + 1;
+    // worth a stage of its own only if it is a small part of the chunk
+    if (head_end > cut[c] && (head_end - cut[c]) * 4 <= cut[c + 1] - cut[c])
+      bound.push_back(head_end);
   }
-  // y rows of chunk d are final after the last chunk that reaches below row1
-  for (int d = 0; d < K; ++d)
-    for (int c = d + 1; c < K; ++c)
-      if (lo[c] < m->chunks[d].row1)
-        m->chunks[d].final_after = c;
+  chunk_first_stage[K] = (int)bound.size();
+  bound.push_back(ns);
+  const int S = (int)bound.size() - 1;
+  std::vector<int> stage_min((size_t)S, INT_MAX);
+  m->stages.resize((size_t)S);
+  for (int j = 0; j < S; ++j) {
+    cfs_matrix_s::Stage &st = m->stages[j];
+    st.slice0 = bound[j];
+    st.slice1 = bound[j + 1];
+    // x rows this stage adds: from where the previous stage stopped up to its
+    // own last row (a row split over two slices stays with the first one)
+    st.x_row0 = j == 0 ? 0 : m->stages[j - 1].x_row1;
+    int hi = st.x_row0 - 1;
+    for (long long i = bound[j]; i < bound[j + 1]; ++i) {
+      hi = max_row[i] > hi ? max_row[i] : hi;
+      stage_min[j] = min_col[i] < stage_min[j] ? min_col[i] : stage_min[j];
+    }
+    st.x_row1 = j + 1 == S ? m->ncols : hi + 1;
+    if (st.x_row1 < st.x_row0)
+      st.x_row1 = st.x_row0;
+  }
+  // y rows of chunk d: [first row of chunk d, first row of chunk d+1); final
+  // after the chunk's own last stage and after the last stage reaching into it
+  for (int d = 0; d < K; ++d) {
+    const int row0 = tag[cut[d]] & kVrowRowMask;
+    const int row1 = d + 1 < K ? (tag[cut[d + 1]] & kVrowRowMask) : m->nrows;
+    int after = chunk_first_stage[d + 1] - 1;
+    for (int j = after + 1; j < S; ++j)
+      if (stage_min[j] < row1)
+        after = j;
+    // a row split across the chunk boundary keeps adding in the next stage
+    if (d + 1 < K && (tag[cut[d + 1]] & kVrowCont) && after < S - 1 &&
+        after < chunk_first_stage[d + 1])
+      after = chunk_first_stage[d + 1];
+    if (row1 > row0)
+      m->stages[after].y_ready.push_back(std::make_pair(row0, row1));
+  }
   return CFS_OK;
 }
 

@@ -522,3 +522,43 @@ def test_value_indexing_is_lossless(gpu, prec, ndistinct):
     # the dictionary changes which bytes are read, not what is computed
     assert cases.normwise_rel_err(y, y0) <= (1e-15 if prec == "d" else 1e-6)
     A.close()
+
+
+@pytest.mark.parametrize("chunks,split", [(8, 1), (8, 0), (3, 1), (16, 1)])
+def test_host_vector_pipeline(gpu, chunks, split):
+    """cfs_cuda_spmv with HOST x and y on a matrix large enough for the staged
+    H2D / kernel / D2H pipeline (>= 4096 slices): pageable vectors (plain
+    enqueue) and pinned ones (the step replayed as a CUDA graph, re-captured
+    when the pointers change), against the oracle"""
+    import torch
+    spec = capi.GenSpec.laplacian(27, 64, 64, 64)
+    rp, ci, v = capi.gen_host_csr(spec)
+    n = len(rp) - 1
+    o = oracle.Oracle(rp, ci, v, 1)
+    capi.set_option("pipeline_chunks", chunks)
+    capi.set_option("pipeline_split", split)
+    try:
+        A = capi.Matrix.from_csr(rp, ci, v)
+        A.tune(1)
+    finally:
+        capi.set_option("pipeline_chunks", 6)
+        capi.set_option("pipeline_split", 1)
+    for seed in (1, 2):
+        x = gen.gen_x(seed, n, np.float64)
+        ref = o.spmv(x)
+        y = np.full(n, -1.0)
+        A.spmv(y, x)                              # pageable
+        assert cases.normwise_rel_err(y, ref) <= 1e-12
+        xp = torch.from_numpy(x).pin_memory()
+        for _ in range(2):                        # new pinned buffers each time
+            yp = torch.full((n,), 7.0, dtype=torch.float64).pin_memory()
+            A.spmv(yp, xp)
+            A.spmv(yp, xp)                        # replay of the captured graph
+            assert cases.normwise_rel_err(yp.numpy(), ref) <= 1e-12
+    # the unpipelined path agrees
+    capi.set_option("pipeline", 0)
+    y0 = np.zeros(n)
+    A.spmv(y0, x)
+    capi.set_option("pipeline", 1)
+    assert cases.normwise_rel_err(y0, ref) <= 1e-12
+    A.close()
