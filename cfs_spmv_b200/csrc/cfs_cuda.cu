@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -396,14 +397,39 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
       set_error("symmetric matrix must be square");
       return CFS_ERR_INVALID;
     }
+    // CFS_GPU_TUNE_REPORT=1: wall time of every preprocessing step on stderr
+    const bool report = getenv("CFS_GPU_TUNE_REPORT") != nullptr;
+    auto now = [&]() {
+      if (report)
+        cudaStreamSynchronize(m->stream);
+      timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    double t0 = now();
+    auto lap = [&](const char *what) {
+      if (!report)
+        return;
+      const double t1 = now();
+      fprintf(stderr, "[tune] %-22s %8.2f ms\n", what, t1 - t0);
+      t0 = t1;
+    };
     CFS_TRY(build_lower(m, m->stream));
+    lap("lower triangle");
     CFS_TRY(build_layout(m, m->stream));
+    lap("sliced layout");
     CFS_TRY(build_windows(m, m->stream));
+    lap("windows (variant 4)");
     CFS_TRY(build_compressed_cols(m, m->stream));
+    lap("index compression");
     CFS_TRY(build_tiles6(m, m->stream));
+    lap("transposed tiles");
     CFS_TRY(build_value_index(m, m->stream));
+    lap("value index");
     CFS_TRY(build_hubs(m, m->stream));
+    lap("hub columns");
     CFS_TRY(build_pipeline_plan(m, m->stream));
+    lap("pipeline plan");
     // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
     m->row_split.assign((size_t)nparts + 1, 0);
     if (nparts > 1) {

@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(kThreads)
     first_real_kernel(long long n, const int *__restrict__ col,
                       unsigned long long *__restrict__ first) {
   const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  if (i < n && col[i] >= 0)
+  // look before reducing: once an early block has answered, the other 100 M
+  // threads must not queue up on the same address
+  if (i < n && col[i] >= 0 &&
+      (unsigned long long)i < *(volatile unsigned long long *)first)
     atomicMin(first, (unsigned long long)i);
 }
 
