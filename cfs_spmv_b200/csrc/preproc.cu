@@ -498,14 +498,14 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
 }
 
 namespace {
-// per slice: smallest column it touches (INT_MAX: none), the row tag of its
-// first lane and the largest row it holds
+// per slice: smallest column it touches (INT_MAX: none), smallest and largest
+// row it holds (INT_MAX / -1: no live lane)
 __global__ void slice_reach_kernel(long long nslices,
                                    const int *__restrict__ slice_ptr,
                                    const int *__restrict__ vrow_row,
                                    const int *__restrict__ sell_col,
                                    int *__restrict__ min_col,
-                                   int *__restrict__ first_tag,
+                                   int *__restrict__ min_row,
                                    int *__restrict__ max_row) {
   const long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -513,7 +513,9 @@ __global__ void slice_reach_kernel(long long nslices,
     return;
   const int p0 = slice_ptr[s], w = slice_ptr[s + 1] - p0;
   const int tag = vrow_row[s * kSliceRows + lane];
-  int lo = INT_MAX, hi = tag >= 0 ? (tag & kVrowRowMask) : -1;
+  int lo = INT_MAX;
+  int rlo = tag >= 0 ? (tag & kVrowRowMask) : INT_MAX;
+  int rhi = tag >= 0 ? (tag & kVrowRowMask) : -1;
   const int *cp = sell_col + (size_t)p0 * kSliceRows + lane;
   for (int k = 0; k < w; ++k) {
     const int c = cp[(size_t)k * kSliceRows];
@@ -522,72 +524,91 @@ __global__ void slice_reach_kernel(long long nslices,
   }
   for (int o = 16; o; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    rlo = min(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+    rhi = max(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
   }
   if (lane == 0) {
     min_col[s] = lo;
-    first_tag[s] = tag;
-    max_row[s] = hi;
+    min_row[s] = rlo;
+    max_row[s] = rhi;
   }
 }
 } // namespace
 
-// Stages of the host-vector pipeline of cfs_cuda_spmv (see cfs_matrix_s::Stage).
-// Only for layouts in natural row order on an unsharded matrix.
+// Stages of the host-vector pipeline of cfs_cuda_spmv (see cfs_matrix_s::Stage),
+// for an unsharded matrix whose slices follow the row order at least block-wise:
+// natural order, or rows length-sorted inside windows (stage boundaries then
+// fall on window boundaries).
 //
 // The slices are cut into pipeline_chunks equal chunks. The y rows of chunk c-1
 // are final once every slice that reaches below the first row of chunk c has
 // run -- in a banded / stencil matrix those are the FIRST few slices of chunk c
-// (its "head": 40 k of 1 M rows for the 27-point Laplacian). So chunk c runs as
-// two stages, head and rest: after the head (which needs only the head's rows
-// of x) the D2H of chunk c-1 starts, while the H2D of the rest of chunk c is
-// still under way. Without the split y lags x by a whole chunk in each
+// (its "head": 40 k of 1.3 M rows for the 27-point Laplacian). So chunk c runs
+// as two stages, head and rest: after the head (which needs only the head's
+// rows of x) the D2H of chunk c-1 starts, while the H2D of the rest of chunk c
+// is still under way. Without the split y lags x by a whole chunk in each
 // direction (tools/e2e_probe.py).
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
   m->stages.clear();
-  if (m->sharded || m->sort_window != 0 || m->nslices < 4096)
+  if (m->sharded || m->nslices < 4096)
     return CFS_OK;
+  // stage boundaries must not cut a sort window
+  const long long unit =
+      m->sort_window == 0 ? 1 : m->sort_window / kSliceRows;
+  if (m->sort_window % kSliceRows != 0 || unit * 64 > m->nslices)
+    return CFS_OK; // globally sorted (power-law matrices): no row order left
   const long long ns = m->nslices;
-  DevArray<int> d_min, d_tag, d_max;
+  DevArray<int> d_min, d_rlo, d_rhi;
   CFS_TRY(d_min.alloc((size_t)ns));
-  CFS_TRY(d_tag.alloc((size_t)ns));
-  CFS_TRY(d_max.alloc((size_t)ns));
+  CFS_TRY(d_rlo.alloc((size_t)ns));
+  CFS_TRY(d_rhi.alloc((size_t)ns));
   slice_reach_kernel<<<blocks_for((size_t)ns * 32), kThreads, 0, s>>>(
-      ns, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p, d_min.p, d_tag.p,
-      d_max.p);
+      ns, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p, d_min.p, d_rlo.p,
+      d_rhi.p);
   CFS_CUDA_TRY(cudaGetLastError());
-  std::vector<int> min_col((size_t)ns), tag((size_t)ns), max_row((size_t)ns);
+  std::vector<int> min_col((size_t)ns), min_row((size_t)ns),
+      max_row((size_t)ns);
   CFS_CUDA_TRY(cudaMemcpyAsync(min_col.data(), d_min.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
-  CFS_CUDA_TRY(cudaMemcpyAsync(tag.data(), d_tag.p, (size_t)ns * 4,
+  CFS_CUDA_TRY(cudaMemcpyAsync(min_row.data(), d_rlo.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
-  CFS_CUDA_TRY(cudaMemcpyAsync(max_row.data(), d_max.p, (size_t)ns * 4,
+  CFS_CUDA_TRY(cudaMemcpyAsync(max_row.data(), d_rhi.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
-  // natural row order: first rows of the slices ascend, every slice starts
-  // with a live lane
-  for (long long i = 0; i < ns; ++i)
-    if (tag[i] < 0 || (i > 0 && (tag[i] & kVrowRowMask) <
-                                    (tag[i - 1] & kVrowRowMask)))
-      return CFS_OK;
   const int K = g_options.pipeline_chunks;
+  auto snap = [&](long long v) { // to a multiple of `unit`
+    return (v + unit / 2) / unit * unit;
+  };
   std::vector<long long> cut((size_t)K + 1);
   for (int c = 0; c <= K; ++c)
-    cut[c] = ns * c / K;
+    cut[c] = c == K ? ns : snap(ns * c / K);
+  for (int c = 0; c < K; ++c)
+    if (cut[c + 1] <= cut[c])
+      return CFS_OK;
+  auto first_row_of = [&](long long s0, long long s1) {
+    int r = INT_MAX;
+    for (long long i = s0; i < s1; ++i)
+      r = min_row[i] < r ? min_row[i] : r;
+    return r;
+  };
   // stage boundaries: chunk starts, and inside chunk c (c >= 1) the end of its
   // head = one past the last slice that reaches below the chunk's first row
   std::vector<long long> bound;
   std::vector<int> chunk_first_stage((size_t)K + 1, 0);
+  std::vector<int> chunk_row0((size_t)K + 1, m->nrows);
   for (int c = 0; c < K; ++c) {
     chunk_first_stage[c] = (int)bound.size();
     bound.push_back(cut[c]);
+    chunk_row0[c] = first_row_of(cut[c], cut[c + 1]);
+    if (chunk_row0[c] == INT_MAX)
+      return CFS_OK;
     if (c == 0 || !g_options.pipeline_split)
       continue;
-    const int first_row = tag[cut[c]] & kVrowRowMask;
     long long head_end = cut[c];
     for (long long i = cut[c]; i < cut[c + 1]; ++i)
-      if (min_col[i] < first_row)
+      if (min_col[i] < chunk_row0[c])
         head_end = i + 1;
+    head_end = (head_end + unit - 1) / unit * unit;
     // worth a stage of its own only if it is a small part of the chunk
     if (head_end > cut[c] && (head_end - cut[c]) * 4 <= cut[c + 1] - cut[c])
       bound.push_back(head_end);
@@ -597,35 +618,41 @@ int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
   const int S = (int)bound.size() - 1;
   std::vector<int> stage_min((size_t)S, INT_MAX);
   m->stages.resize((size_t)S);
+  int prev_hi = -1;
   for (int j = 0; j < S; ++j) {
     cfs_matrix_s::Stage &st = m->stages[j];
     st.slice0 = bound[j];
     st.slice1 = bound[j + 1];
-    // x rows this stage adds: from where the previous stage stopped up to its
-    // own last row (a row split over two slices stays with the first one)
-    st.x_row0 = j == 0 ? 0 : m->stages[j - 1].x_row1;
-    int hi = st.x_row0 - 1;
+    int lo = INT_MAX, hi = -1;
     for (long long i = bound[j]; i < bound[j + 1]; ++i) {
+      lo = min_row[i] < lo ? min_row[i] : lo;
       hi = max_row[i] > hi ? max_row[i] : hi;
       stage_min[j] = min_col[i] < stage_min[j] ? min_col[i] : stage_min[j];
     }
+    // the stages have to follow the row order (a row split over a boundary
+    // may appear on both sides)
+    if (hi < 0 || lo < prev_hi) {
+      m->stages.clear();
+      return CFS_OK;
+    }
+    prev_hi = hi;
+    // x rows this stage adds: from where the previous stage stopped up to its
+    // own last row
+    st.x_row0 = j == 0 ? 0 : m->stages[j - 1].x_row1;
     st.x_row1 = j + 1 == S ? m->ncols : hi + 1;
     if (st.x_row1 < st.x_row0)
       st.x_row1 = st.x_row0;
   }
   // y rows of chunk d: [first row of chunk d, first row of chunk d+1); final
-  // after the chunk's own last stage and after the last stage reaching into it
+  // after the chunk's own last stage, after a row shared with the next chunk
+  // has received all its parts, and after the last stage reaching into it
   for (int d = 0; d < K; ++d) {
-    const int row0 = tag[cut[d]] & kVrowRowMask;
-    const int row1 = d + 1 < K ? (tag[cut[d + 1]] & kVrowRowMask) : m->nrows;
+    const int row0 = d == 0 ? 0 : chunk_row0[d];
+    const int row1 = d + 1 < K ? chunk_row0[d + 1] : m->nrows;
     int after = chunk_first_stage[d + 1] - 1;
     for (int j = after + 1; j < S; ++j)
       if (stage_min[j] < row1)
         after = j;
-    // a row split across the chunk boundary keeps adding in the next stage
-    if (d + 1 < K && (tag[cut[d + 1]] & kVrowCont) && after < S - 1 &&
-        after < chunk_first_stage[d + 1])
-      after = chunk_first_stage[d + 1];
     if (row1 > row0)
       m->stages[after].y_ready.push_back(std::make_pair(row0, row1));
   }

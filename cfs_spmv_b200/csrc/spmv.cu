@@ -301,7 +301,10 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
 
 template <typename T, bool HALO, bool DOT>
 int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-                    double *dot, cudaStream_t s) {
+                    double *dot, cudaStream_t s, long long s0, long long s1) {
+  // whole tiles only: [s0, s1) starts on a tile boundary (the caller checks)
+  const long long tile0 = s0 / kT6Slices;
+  const long long ntiles = (s1 - s0 + kT6Slices - 1) / kT6Slices;
   auto kernel = tile6::sym_spmv_tile_kernel<T, HALO, DOT>;
   const int smem = m->t6_smem_entries * (int)sizeof(T);
   static int granted = 0; // per instantiation
@@ -310,8 +313,8 @@ int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
         kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT6MaxSmemBytes));
     granted = kT6MaxSmemBytes;
   }
-  kernel<<<(unsigned)m->nt6, tile6::kThreads, smem, s>>>(
-      m->nslices, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->t6_pack.p,
+  kernel<<<(unsigned)ntiles, tile6::kThreads, smem, s>>>(
+      tile0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->t6_pack.p,
       (const T *)m->sell_val.p, (const T *)m->diagonal.p, m->t6_lo.p,
       m->t6_ncols.p, m->t6_cptr_off.p, m->t6_cptr.p, xb, yb, y_lower, dot);
   return CFS_OK;
@@ -319,12 +322,14 @@ int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
 
 template <typename T>
 int launch_tile6(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-                 double *dot, cudaStream_t s) {
+                 double *dot, cudaStream_t s, long long s0, long long s1) {
   if (y_lower)
-    return launch_tile6_as<T, true, false>(m, xb, yb, y_lower, nullptr, s);
+    return launch_tile6_as<T, true, false>(m, xb, yb, y_lower, nullptr, s, s0,
+                                           s1);
   if (dot)
-    return launch_tile6_as<T, false, true>(m, xb, yb, nullptr, dot, s);
-  return launch_tile6_as<T, false, false>(m, xb, yb, nullptr, nullptr, s);
+    return launch_tile6_as<T, false, true>(m, xb, yb, nullptr, dot, s, s0, s1);
+  return launch_tile6_as<T, false, false>(m, xb, yb, nullptr, nullptr, s, s0,
+                                          s1);
 }
 
 template <typename T>
@@ -347,9 +352,11 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   const bool partial = s0 != 0 || s1 != m->nslices;
   // bounded column windows (banded / FEM orderings): products transposed
   // through shared memory, one coalesced RED per column and tile
+  // (slice ranges of the host-vector pipeline: whole tiles only)
   if ((variant == 5 || variant == 6) && m->nt6 > 0 && g_options.tile6 &&
-      !partial && mode == 0 && !(yl && dot))
-    return launch_tile6<T>(m, xb, yb, yl, dot, s);
+      mode == 0 && !(yl && dot) && s0 % kT6Slices == 0 &&
+      (s1 % kT6Slices == 0 || s1 == m->nslices))
+    return launch_tile6<T>(m, xb, yb, yl, dot, s, s0, s1);
   if ((yl || partial || dot) && variant != 1)
     variant = 5; // halo fusion / slice ranges / x'Ax exist in the register kernels
   // bulk copies of the x / y windows need 16-byte aligned vectors

@@ -56,7 +56,7 @@ __device__ __forceinline__ unsigned ld_stream(const unsigned *p) {
 // tried and lost to its own register spills (485 us vs 421 us).
 template <typename T, bool HALO, bool DOT>
 __global__ void __launch_bounds__(kThreads, 2)
-    sym_spmv_tile_kernel(long long nslices, int row_begin,
+    sym_spmv_tile_kernel(long long tile_begin, long long nslices, int row_begin,
                          const int *__restrict__ slice_ptr,
                          const int *__restrict__ vrow_row,
                          const unsigned *__restrict__ pack,
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *prod = reinterpret_cast<T *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tile = blockIdx.x;
+  const long long tile = tile_begin + blockIdx.x;
   const long long s = tile * kT6Slices + warp;
   const int lo = tile_lo[tile];
 

@@ -524,14 +524,18 @@ def test_value_indexing_is_lossless(gpu, prec, ndistinct):
     A.close()
 
 
+@pytest.mark.parametrize("kind", ["lap27", "banded"])
 @pytest.mark.parametrize("chunks,split", [(8, 1), (8, 0), (3, 1), (16, 1)])
-def test_host_vector_pipeline(gpu, chunks, split):
+def test_host_vector_pipeline(gpu, chunks, split, kind):
     """cfs_cuda_spmv with HOST x and y on a matrix large enough for the staged
     H2D / kernel / D2H pipeline (>= 4096 slices): pageable vectors (plain
     enqueue) and pinned ones (the step replayed as a CUDA graph, re-captured
     when the pointers change), against the oracle"""
     import torch
-    spec = capi.GenSpec.laplacian(27, 64, 64, 64)
+    # lap27: natural row order, variant 5; banded: rows length-sorted inside
+    # 1024-row windows, split virtual rows, the tile kernel on slice ranges
+    spec = (capi.GenSpec.laplacian(27, 64, 64, 64) if kind == "lap27"
+            else capi.GenSpec.banded(300000, 2000, 152, 7))
     rp, ci, v = capi.gen_host_csr(spec)
     n = len(rp) - 1
     o = oracle.Oracle(rp, ci, v, 1)
