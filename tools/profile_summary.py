@@ -88,6 +88,40 @@ def details(tag, rep, kname, traffic_name="traffic.json"):
         "source": "ncu --set full --clock-control none, %s" % os.path.basename(rep),
     }
     json.dump(t, open(os.path.join(OUT, traffic_name), "w"), indent=1)
+    # gather / atomic counters of the first captured launch (north star: L2 hit
+    # rate of the x gathers, atomic / replay counters)
+    wanted = [
+        "lts__t_sector_hit_rate.pct",
+        "lts__t_sector_op_read_hit_rate.pct",
+        "lts__t_sector_op_red_hit_rate.pct",
+        "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+        "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
+        "l1tex__t_sector_hit_rate.pct",
+        "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum",
+        "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum",
+        "l1tex__data_pipe_lsu_wavefronts.sum",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
+        "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__time_duration.sum",
+    ]
+    first = raw[2]
+    counters = {}
+    for name in wanted:
+        if name in hdr:
+            counters[name] = {"value": first[hdr.index(name)],
+                              "unit": raw[1][hdr.index(name)]}
+    json.dump(counters, open(os.path.join(
+        OUT, "%s_%s_counters.json" % (tag, kname)), "w"), indent=1)
     # hot SASS
     src = list(csv.reader(io.StringIO(ncu_page(rep, "source"))))
     for idx, r in enumerate(src[:10]):
