@@ -35,6 +35,8 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
     "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_halo_async",
     "cfs_cuda_spmv_timed", "cfs_cuda_cg_solve",
+    "cfs_cuda_spmv_halo_dot_async", "cfs_cuda_cg_update_xr",
+    "cfs_cuda_cg_update_p",
     "cfs_cuda_matrix_export",
     "cfs_gen_host_count", "cfs_gen_host_fill", "cfs_gen_host_x",
     "cfs_cuda_gen_count", "cfs_cuda_gen_fill", "cfs_cuda_gen_x",
@@ -194,6 +196,11 @@ def lib():
                                          ctypes.POINTER(sz)]
     L.cfs_cuda_cg_solve.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_double,
                                     ctypes.POINTER(CgResult), vp, ctypes.c_int]
+    L.cfs_cuda_spmv_halo_dot_async.argtypes = [vp, vp, vp, vp, ctypes.c_int,
+                                               vp, vp]
+    L.cfs_cuda_cg_update_xr.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp, vp,
+                                        vp, vp]
+    L.cfs_cuda_cg_update_p.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp]
     gs = ctypes.POINTER(GenSpec)
     L.cfs_gen_host_count.argtypes = [gs, i64, i64, vp]
     L.cfs_gen_host_fill.argtypes = [gs, i64, i64, vp, vp, vp, ctypes.c_int]
@@ -341,6 +348,13 @@ class Matrix:
             out["history"] = hist[:res.iterations + 1]
         return out
 
+    def spmv_halo_dot_async(self, y_dev, x_dev, y_lower_base, y_is_zero,
+                            dot_dev, stream=0):
+        """spmv_halo_async that also adds this shard's x'(A x) to *dot_dev"""
+        check(lib().cfs_cuda_spmv_halo_dot_async(
+            self._h, _ptr(y_dev), _ptr(x_dev), y_lower_base, int(y_is_zero),
+            _ptr(dot_dev), stream))
+
     def spmv_timed(self, y_dev, x_dev, iters, stream=0):
         """-> (total_ms, kernel_ms) summed over `iters` SpMVs"""
         total, kern = ctypes.c_float(0), ctypes.c_float(0)
@@ -394,6 +408,17 @@ class Matrix:
 
 
 # ---- synthetic inputs ------------------------------------------------------
+def cg_update_xr(n, is_double, scal, p, q, x, r, rr_next, stream=0):
+    check(lib().cfs_cuda_cg_update_xr(n, int(is_double), _ptr(scal), _ptr(p),
+                                      _ptr(q), _ptr(x), _ptr(r), _ptr(rr_next),
+                                      stream))
+
+
+def cg_update_p(n, is_double, scal, r, p, stream=0):
+    check(lib().cfs_cuda_cg_update_p(n, int(is_double), _ptr(scal), _ptr(r),
+                                     _ptr(p), stream))
+
+
 def gen_host_csr(spec, row_begin=0, row_end=None, dtype=np.float64):
     """full CSR of rows [row_begin,row_end) on the host (no GPU needed)"""
     row_end = spec.nrows if row_end is None else row_end

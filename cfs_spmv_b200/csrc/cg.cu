@@ -168,6 +168,56 @@ __global__ void cg_rotate_kernel(CgState *st, double *history,
   }
 }
 
+// ---- the same updates for a row shard: the scalars are global sums the
+// caller has reduced across the ranks (scal = {r'r, p'Ap, next r'r})
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    shard_update_xr_kernel(long long n, const double *__restrict__ scal,
+                           const T *__restrict__ p, const T *__restrict__ q,
+                           T *__restrict__ x, T *__restrict__ r,
+                           double *__restrict__ rr_next) {
+  __shared__ double scratch[kThreads / 32];
+  const double pq = scal[1];
+  const double alpha = pq > 0.0 ? scal[0] / pq : 0.0;
+  double local = 0;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads) {
+    x[i] = (T)((double)x[i] + alpha * (double)p[i]);
+    const T ri = (T)((double)r[i] - alpha * (double)q[i]);
+    r[i] = ri;
+    local += (double)ri * (double)ri;
+  }
+  local = block_sum(local, scratch);
+  if (threadIdx.x == 0)
+    atomicAdd(rr_next, local);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    shard_update_p_kernel(long long n, const double *__restrict__ scal,
+                          const T *__restrict__ r, T *__restrict__ p) {
+  const double beta = scal[0] > 0.0 ? scal[2] / scal[0] : 0.0;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads)
+    p[i] = (T)((double)r[i] + beta * (double)p[i]);
+}
+
+// *out += sum of the partial sums the SpMV kernel left; the slots are cleared
+__global__ void dot_collect_kernel(double *__restrict__ slots,
+                                   double *__restrict__ out) {
+  const int t = threadIdx.x;
+  double part = 0;
+  for (int k = t; k < reg::kDotSlots; k += 32) {
+    part += slots[k * reg::kDotStride];
+    slots[k * reg::kDotStride] = 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+    part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (t == 0)
+    *out += part;
+}
+
 int grid_for(long long n) {
   static int sms = 0;
   if (!sms) {
@@ -352,5 +402,71 @@ extern "C" int cfs_cuda_cg_solve(cfs_mat_t m, void *x, const void *b,
     return status;
   if (x_host)
     CFS_CUDA_TRY(cudaMemcpy(x, xd.p, bytes, cudaMemcpyDeviceToHost));
+  return CFS_OK;
+}
+
+
+extern "C" int cfs_cuda_spmv_halo_dot_async(cfs_mat_t m, void *y_dev,
+                                            const void *x_dev,
+                                            void *y_lower_base, int y_is_zero,
+                                            double *dot_dev, void *stream) {
+  if (!m || !y_dev || !x_dev || !dot_dev)
+    return CFS_ERR_INVALID;
+  if (!m->tuned || !m->symmetric) {
+    set_error("cfs_cuda_spmv_halo_dot_async: needs a tuned symmetric matrix");
+    return CFS_ERR_STATE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!m->dot_slots.p) {
+    CFS_TRY(m->dot_slots.alloc(kDotWords));
+    CFS_CUDA_TRY(cudaMemsetAsync(m->dot_slots.p, 0, kDotWords * 8, s));
+  }
+  CFS_TRY(launch_sym_spmv(m, y_dev, x_dev, s, nullptr, nullptr, y_lower_base,
+                          y_is_zero != 0, 0, -1, m->dot_slots.p));
+  dot_collect_kernel<<<1, 32, 0, s>>>(m->dot_slots.p, dot_dev);
+  CFS_CUDA_TRY(cudaGetLastError());
+  return CFS_OK;
+}
+
+extern "C" int cfs_cuda_cg_update_xr(int64_t n, int is_double,
+                                     const double *scal, const void *p,
+                                     const void *q, void *x, void *r,
+                                     double *rr_next_dev, void *stream) {
+  if (n < 0 || !scal || !p || !q || !x || !r || !rr_next_dev)
+    return CFS_ERR_INVALID;
+  CFS_TRY(require_device());
+  if (n == 0)
+    return CFS_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = grid_for(n);
+  if (is_double)
+    shard_update_xr_kernel<double><<<grid, kThreads, 0, s>>>(
+        n, scal, (const double *)p, (const double *)q, (double *)x,
+        (double *)r, rr_next_dev);
+  else
+    shard_update_xr_kernel<float><<<grid, kThreads, 0, s>>>(
+        n, scal, (const float *)p, (const float *)q, (float *)x, (float *)r,
+        rr_next_dev);
+  CFS_CUDA_TRY(cudaGetLastError());
+  return CFS_OK;
+}
+
+extern "C" int cfs_cuda_cg_update_p(int64_t n, int is_double,
+                                    const double *scal, const void *r, void *p,
+                                    void *stream) {
+  if (n < 0 || !scal || !r || !p)
+    return CFS_ERR_INVALID;
+  CFS_TRY(require_device());
+  if (n == 0)
+    return CFS_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = grid_for(n);
+  if (is_double)
+    shard_update_p_kernel<double><<<grid, kThreads, 0, s>>>(
+        n, scal, (const double *)r, (double *)p);
+  else
+    shard_update_p_kernel<float><<<grid, kThreads, 0, s>>>(
+        n, scal, (const float *)r, (float *)p);
+  CFS_CUDA_TRY(cudaGetLastError());
   return CFS_OK;
 }

@@ -194,6 +194,8 @@ struct cfs_matrix_s {
   cfsb::DevArray<int32_t> weight, adj_ptr, adj, color_first, color;
   cfsb::DevArray<int32_t> range_ptr, part_nranges, range_start, range_end;
 
+  // partial sums of x'(A x) (cfs_cuda_spmv_halo_dot_async)
+  cfsb::DevArray<double> dot_slots;
   // staging for the synchronous host-pointer entry point
   cfsb::DevArray<char> stage_x, stage_y;
   cudaStream_t stream = nullptr;

@@ -184,7 +184,13 @@ void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   // hub columns: flagged column stream + a second, column-wise kernel
   const bool hubs = MODE == 0 && !y_lower && m->nhubs > 0 && g_options.hubs &&
                     s0 == 0 && s1 == m->nslices;
-  if (y_lower)
+  if (y_lower && dot)
+    sym_spmv_sell_kernel<T, 0, true, false, true>
+        <<<grid, kSpmvThreads, 0, s>>>(
+            s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
+            (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower,
+            dot);
+  else if (y_lower)
     sym_spmv_sell_kernel<T, MODE, true, false><<<grid, kSpmvThreads, 0, s>>>(
         s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
         (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower,
@@ -286,7 +292,9 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
     else                                                                       \
       CFS_LAUNCH_REG(HALO, DOT, 0, SMEM, YL, DOTP);                            \
   } while (0)
-  if (y_lower)
+  if (y_lower && dot)
+    CFS_LAUNCH_REG_VI(true, true, 0, y_lower, dot);
+  else if (y_lower)
     CFS_LAUNCH_REG_VI(true, false, 0, y_lower, nullptr);
   else if (dot)
     CFS_LAUNCH_REG_VI(false, true, 0, nullptr, dot);
@@ -323,6 +331,8 @@ int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
 template <typename T>
 int launch_tile6(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
                  double *dot, cudaStream_t s, long long s0, long long s1) {
+  if (y_lower && dot)
+    return launch_tile6_as<T, true, true>(m, xb, yb, y_lower, dot, s, s0, s1);
   if (y_lower)
     return launch_tile6_as<T, true, false>(m, xb, yb, y_lower, nullptr, s, s0,
                                            s1);
@@ -354,7 +364,7 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   // through shared memory, one coalesced RED per column and tile
   // (slice ranges of the host-vector pipeline: whole tiles only)
   if ((variant == 5 || variant == 6) && m->nt6 > 0 && g_options.tile6 &&
-      mode == 0 && !(yl && dot) && s0 % kT6Slices == 0 &&
+      mode == 0 && s0 % kT6Slices == 0 &&
       (s1 % kT6Slices == 0 || s1 == m->nslices))
     return launch_tile6<T>(m, xb, yb, yl, dot, s, s0, s1);
   if ((yl || partial || dot) && variant != 1)

@@ -293,3 +293,104 @@ class ShardedSpMV:
         ms = (time.perf_counter() - t0) * 1e3
         return ms, x_host.numel() * x_host.element_size(), \
             y_host.numel() * y_host.element_size()
+
+
+class DistributedCG:
+    """Conjugate gradients over the row shards of a ShardedSpMV (fused NVLink
+    halo only): A x = b with x, r, p, q sharded like the rows.
+
+    Per iteration: q = A p with the halo reduction fused into the kernel AND
+    this shard's part of p'Ap coming out of it (cfs_cuda_spmv_halo_dot_async);
+    a 1-double all-reduce; x += a p, r -= a q, r'r (cfs_cuda_cg_update_xr); a
+    1-double all-reduce; p = r + b p (cfs_cuda_cg_update_p). The all-reduces are
+    the exchange step conjugate gradients really have; torch.distributed is
+    the plumbing for them. p lives in the symmetric x buffer of the halo
+    exchange, so the neighbours pull its halo like any x."""
+
+    def __init__(self, op):
+        import torch
+        if op.world > 1 and op.p2p is None:
+            raise RuntimeError("DistributedCG needs the fused NVLink halo")
+        self.op = op
+        self.n = op.e - op.b
+        self.off = op.b - op.h          # halo rows in front of the owned ones
+        dt = op.x_ext.dtype
+        dev = op.x_ext.device
+        self.is_double = dt == torch.float64
+        self.x = torch.zeros(self.n, dtype=dt, device=dev)
+        self.r = torch.zeros(self.n, dtype=dt, device=dev)
+        # {r'r, p'Ap, next r'r} as global sums, + the local parts before the
+        # all-reduce
+        self.scal = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def _allreduce(self, t):
+        import torch.distributed as dist
+        if self.op.world > 1:
+            dist.all_reduce(t)
+
+    def _spmv_dot(self, stream):
+        """q = A p (result in op.y_ext), scal[1] = p'Ap (global)"""
+        op = self.op
+        self.scal[1:2].zero_()
+        if op.p2p is not None:
+            p2p = op.p2p
+            p2p.y_ext.zero_()
+            p2p.hy.barrier()
+            if p2p.x_peer is not None:
+                p2p.x_ext[:p2p.nhalo].copy_(p2p.x_peer)
+            op.matrix.spmv_halo_dot_async(p2p.y_ext, p2p.x_ext,
+                                          p2p.y_lower_base, True,
+                                          self.scal[1:2], stream)
+            p2p.hy.barrier()
+        else:
+            op.y_ext.zero_()
+            op.matrix.spmv_halo_dot_async(op.y_ext, op.x_ext, None, True,
+                                          self.scal[1:2], stream)
+        self._allreduce(self.scal[1:2])
+
+    def solve(self, b, max_iters, rel_tol, x0=None, check_every=10):
+        """b, x0: this rank's OWNED rows (device tensors). Returns a dict;
+        the solution stays in self.x."""
+        import torch
+        from . import capi
+        op = self.op
+        stream = torch.cuda.current_stream().cuda_stream
+        p_own = op.x_ext[self.off:]
+        self.x.zero_()
+        if x0 is not None:
+            self.x.copy_(x0)
+        # r = b - A x0
+        p_own.copy_(self.x)
+        self._spmv_dot(stream)
+        self.r.copy_(b - op.y_ext[self.off:])
+        p_own.copy_(self.r)
+        self.scal[0:1].copy_((self.r.double() * self.r.double()).sum().reshape(1))
+        self._allreduce(self.scal[0:1])
+        rr0 = float(self.scal[0].item())
+        tol2 = rel_tol * rel_tol * rr0
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        it, rr, converged, breakdown = 0, rr0, rr0 == 0.0, False
+        while it < max_iters and not converged and not breakdown:
+            self._spmv_dot(stream)
+            self.scal[2:3].zero_()
+            capi.cg_update_xr(self.n, self.is_double, self.scal, p_own,
+                              op.y_ext[self.off:], self.x, self.r,
+                              self.scal[2:3], stream)
+            self._allreduce(self.scal[2:3])
+            capi.cg_update_p(self.n, self.is_double, self.scal, self.r, p_own,
+                             stream)
+            self.scal[0:1].copy_(self.scal[2:3])
+            it += 1
+            if it % check_every == 0 or it == max_iters:
+                vals = self.scal.tolist()
+                rr = vals[0]
+                breakdown = not (vals[1] > 0.0)
+                converged = rr <= tol2
+        e1.record()
+        torch.cuda.synchronize()
+        return {"iterations": it, "converged": bool(converged),
+                "breakdown": bool(breakdown),
+                "initial_residual_norm": rr0 ** 0.5,
+                "residual_norm": max(rr, 0.0) ** 0.5,
+                "ms_total": e0.elapsed_time(e1)}

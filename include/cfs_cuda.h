@@ -218,6 +218,28 @@ int cfs_cuda_cg_solve(cfs_mat_t m, void *x, const void *b, int max_iters,
                       double rel_tol, cfs_cg_result *result, double *history,
                       int history_capacity);
 
+/* Building blocks of the same loop over row SHARDS (one process per GPU): the
+ * caller sums the two scalars of an iteration across its ranks (a 1-double
+ * all-reduce each: the exchange step conjugate gradients really have) and the
+ * vector work stays in these kernels. cfs_spmv_b200/dist.py (DistributedCG) is
+ * the loop.
+ *   cfs_cuda_spmv_halo_dot_async: cfs_cuda_spmv_halo_async that also ADDS this
+ *     shard's part of x'(A x) to *dot_dev (every stored entry lives in exactly
+ *     one shard, so the parts add up to the global value);
+ *   cfs_cuda_cg_update_xr: alpha = scal[0] / scal[1] (r'r, p'Ap: global sums);
+ *     x += alpha p, r -= alpha q, *rr_next_dev += this shard's r'r;
+ *   cfs_cuda_cg_update_p: beta = scal[2] / scal[0]; p = r + beta p.
+ * All pointers are device pointers over the shard's OWNED rows (n of them);
+ * scal is a device array of 3 doubles {r'r, p'Ap, next r'r}. */
+int cfs_cuda_spmv_halo_dot_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                                 void *y_lower_base, int y_is_zero,
+                                 double *dot_dev, void *stream);
+int cfs_cuda_cg_update_xr(int64_t n, int is_double, const double *scal,
+                          const void *p, const void *q, void *x, void *r,
+                          double *rr_next_dev, void *stream);
+int cfs_cuda_cg_update_p(int64_t n, int is_double, const double *scal,
+                         const void *r, void *p, void *stream);
+
 /* Measurement aid for bench.py (bench_spmv_mmf.cpp:162-167 times the same
  * loop with omp_get_wtime): runs `iters` SpMVs on `stream` and returns the
  * summed device time of the SpMV KERNEL alone (kernel_ms, CUDA events placed

@@ -14,7 +14,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from cfs_spmv_b200 import capi, gen  # noqa: E402
-from cfs_spmv_b200.dist import ShardedSpMV  # noqa: E402
+from cfs_spmv_b200.dist import DistributedCG, ShardedSpMV  # noqa: E402
 
 
 def main():
@@ -49,6 +49,31 @@ def main():
                 world, mode, "p2p" if op.p2p is not None else "nccl",
                 spec.kind, "f64" if dbl else "f32", err,
                 "OK" if ok else "FAIL"), flush=True)
+            failures += not ok
+    # conjugate gradients over the shards (fused halo only): A x = A xs
+    if mode == "p2p":
+        for spec, dbl, tol, xtol in (
+                (capi.GenSpec.laplacian(27, 40, 40, 16 * world), True, 1e-10, 1e-7),
+                (capi.GenSpec.banded(20000 * world, 700, 152, 3), False, 1e-5, 1e-3)):
+            op = ShardedSpMV(spec, rank, world, is_double=dbl, xseed=9)
+            if op.p2p is None:
+                continue
+            xs = op.x_ext[op.b - op.h:].clone()   # the solution to find
+            op.step()
+            b = op.y_owned().clone()               # b = A xs
+            cg = DistributedCG(op)
+            res = cg.solve(b, 3000, tol)
+            num = ((cg.x - xs).double() ** 2).sum().reshape(1)
+            den = (xs.double() ** 2).sum().reshape(1)
+            dist.all_reduce(num)
+            dist.all_reduce(den)
+            err = float((num / den).sqrt().item())
+            ok = res["converged"] and err <= xtol
+            if rank == 0:
+                print("multi-gpu cg world=%d kind=%d %s: %d iterations, error "
+                      "%.3e %s" % (world, spec.kind, "f64" if dbl else "f32",
+                                   res["iterations"], err,
+                                   "OK" if ok else "FAIL"), flush=True)
             failures += not ok
     dist.barrier()
     dist.destroy_process_group()

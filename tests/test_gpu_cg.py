@@ -144,3 +144,26 @@ def test_cg_on_a_ragged_matrix(gpu):
     assert res["converged"] == 1
     assert np.linalg.norm(x - xs) <= 1e-9 * np.linalg.norm(xs)
     A.close()
+
+
+def test_distributed_cg_building_blocks_on_one_gpu(gpu):
+    """the shard loop (DistributedCG: spmv_halo_dot + update_xr + update_p, the
+    scalars reduced by the caller) at world size 1 gives what cfs_cuda_cg_solve
+    gives; the multi-GPU run of the same loop is tests/test_gpu_multi.py"""
+    import torch
+    from cfs_spmv_b200.dist import DistributedCG, ShardedSpMV
+    spec = capi.GenSpec.laplacian(27, 40, 40, 40)
+    op = ShardedSpMV(spec, 0, 1, is_double=True, xseed=3)
+    n = spec.nrows
+    xs = op.x_ext.clone()
+    op.step()
+    b = op.y_owned().clone()
+    cg = DistributedCG(op)
+    res = cg.solve(b, 3000, 1e-10, check_every=1)
+    assert res["converged"] and not res["breakdown"]
+    err = (torch.linalg.norm(cg.x - xs) / torch.linalg.norm(xs)).item()
+    assert err <= 1e-7
+    x2 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    ref = op.matrix.cg_solve(x2, b, 3000, 1e-10)
+    assert abs(res["iterations"] - ref["iterations"]) <= 2
+    assert (torch.linalg.norm(cg.x - x2) / torch.linalg.norm(x2)).item() <= 1e-8

@@ -29,4 +29,8 @@ def test_sharded_spmv_matches_oracle(gpu, world, halo):
         capture_output=True, text=True, timeout=600,
         env=dict(os.environ, CFS_GPU_HALO=halo))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count(" OK") == 3 and "FAIL" not in r.stdout
+    assert "FAIL" not in r.stdout
+    assert r.stdout.count("err=") == 3 and r.stdout.count(" OK") >= 3
+    if halo == "p2p" and "P2P halo unavailable" not in r.stdout:
+        # + conjugate gradients over the shards, double and single
+        assert r.stdout.count("multi-gpu cg") == 2, r.stdout[-2000:]
