@@ -53,15 +53,31 @@ int cfs_cuda_device_count(int *count);
 int cfs_cuda_init(int device);
 const char *cfs_cuda_last_error(void);
 const char *cfs_cuda_version(void);
-/* run-time tunables (the CFS_GPU_* knobs): "spmv_variant" 1 = one warp per
- * slice with direct loads, 2 = persistent TMA-staged kernel, 4 = shared-memory
- * x/y windows, 5 = compressed index stream + shuffle-merged REDs (default; on
- * matrices with bounded column windows it hands over to 6 = transposed term
- * transposed through shared memory, "tile6" 0 switches that off); "value_index" 0/1: dictionary-coded values
- * for regular matrices with <= 256 distinct values (lossless, default 1);
- * "sort_rows", "pipeline", "hubs" 0/1;
- * "ctas_per_sm" for the persistent kernel. Returns CFS_ERR_INVALID for an
- * unknown key. */
+/* run-time tunables; unknown key or bad value: CFS_ERR_INVALID.
+ *   "spmv_variant"   1 = one warp per slice, direct loads; 2 = persistent
+ *                    TMA-staged kernel; 4 = shared-memory x/y windows; 5 =
+ *                    compressed index stream + shuffle-merged REDs (default; on
+ *                    irregular matrices with bounded column windows it hands
+ *                    over to 6); 6 = transposed term transposed through shared
+ *                    memory
+ *   "tile6"          0/1  allow variant 6 (read at tune and at launch time)
+ *   "value_index"    0/1  dictionary-coded values where the lower triangle has
+ *                    <= 256 distinct values (lossless; tune and launch time)
+ *   "sort_rows", "rechunk", "rechunk_pct", "hubs"   layout of ragged matrices
+ *                    (tune time): length-sorting, virtual rows of rechunk_pct %
+ *                    of the mean row length, column-wise hub columns
+ *   "csr_layout"     0/1  Format::csr streams the sliced layout (default) or
+ *                    runs the warp-per-row comparator kernel
+ *   "pipeline", "pipeline_chunks", "pipeline_split", "pipeline_graph"
+ *                    host-vector path of cfs_cuda_spmv: staged H2D / kernel /
+ *                    D2H pipeline, its chunk count, head + rest stages, replay
+ *                    as one CUDA graph
+ *   "cg_batch"       iterations cfs_cuda_cg_solve enqueues between two looks
+ *                    at the stop flag
+ *   "ctas_per_sm"    persistent kernel (variant 2)
+ *   "diag_mode", "pipeline_skip", "pipeline_smem", "pipeline_trace"
+ *                    measurement aids (non-zero diag_mode / pipeline_skip
+ *                    compute WRONG results) */
 int cfs_cuda_set_option(const char *key, long long value);
 
 /* ---- allocator: backs internal_alloc / internal_free
