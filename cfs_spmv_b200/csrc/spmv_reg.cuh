@@ -62,7 +62,9 @@ using cfsb::kDotStride;
 // Tried and dropped for the value-indexed instantiations: software-pipelining
 // the x gathers of the next chain behind the shuffles / REDs of the current one
 // (the kernel waits on those gathers once the value stream is gone). At the 32
-// registers that 64 warps/SM allow it spills, and lost: 152 -> 189 us.
+// registers that 64 warps/SM allow it spills, and lost: 152 -> 189 us; at 40
+// registers (48 warps/SM, no spills) it lost too: 172 us. More warps beat more
+// loads in flight per warp, again.
 //
 // VI (value indexing, valindex.cu): 0 = values are streamed (8 bytes/entry),
 // 1 = one byte per entry names the value in a dictionary of <= 256 distinct
