@@ -145,12 +145,19 @@ template <typename T> int build_typed(cfs_matrix_s *m, cudaStream_t s) {
     DevArray<unsigned long long> first;
     CFS_TRY(first.alloc(1));
     CFS_CUDA_TRY(cudaMemsetAsync(first.p, 0xff, 8, s));
-    first_real_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0,
-                        s>>>(n, col, first.p);
-    CFS_CUDA_TRY(cudaGetLastError());
-    unsigned long long at = 0;
-    CFS_CUDA_TRY(cudaMemcpyAsync(&at, first.p, 8, cudaMemcpyDeviceToHost, s));
-    CFS_CUDA_TRY(cudaStreamSynchronize(s));
+    unsigned long long at = ~0ULL;
+    // it is almost always among the first few entries: look there first
+    for (long long span = n < kSample ? n : kSample; at == ~0ULL;) {
+      first_real_kernel<<<(unsigned)((span + kThreads - 1) / kThreads),
+                          kThreads, 0, s>>>(span, col, first.p);
+      CFS_CUDA_TRY(cudaGetLastError());
+      CFS_CUDA_TRY(cudaMemcpyAsync(&at, first.p, 8, cudaMemcpyDeviceToHost,
+                                   s));
+      CFS_CUDA_TRY(cudaStreamSynchronize(s));
+      if (span == n)
+        break;
+      span = n;
+    }
     if (at == ~0ULL)
       return CFS_OK; // no stored lower entry at all
     CFS_CUDA_TRY(cudaMemcpy(&filler, val + at, sizeof(U),
