@@ -522,7 +522,8 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
   info->index_rows = m->ccol_rows;
   info->value_dictionary = m->ndict;
   info->transposed_tiles = m->nt6;
-  info->tile_smem_bytes = (int64_t)m->t6_smem_entries * vs;
+  info->tile_smem_bytes = (int64_t)((m->t6_smem_entries + 7) & ~7) * vs +
+                          (m->nt6 ? (m->t6_max_cols + 2) * 2 : 0);
   if (m->symmetric && m->tuned) {
     // size(), csr_matrix.tpp:191-228 (including its (nrows + 1*nthreads) term)
     int64_t s = ((int64_t)m->nrows + 1LL * m->nparts) * 4;

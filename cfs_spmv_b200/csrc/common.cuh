@@ -174,6 +174,7 @@ struct cfs_matrix_s {
   // variant 6: column-transposed tiles (tiles6.cu); nt6 == 0: not applicable
   int64_t nt6 = 0;
   int t6_smem_entries = 0;                  // products of the largest tile
+  int t6_max_cols = 0;                      // widest column window of a tile
   int64_t t6_cptr_entries = 0;
   cfsb::DevArray<unsigned> t6_pack;         // padded_entries: lcol | slot << 16
   cfsb::DevArray<int> t6_lo, t6_ncols;      // per tile: first column, columns

@@ -314,17 +314,21 @@ int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   const long long tile0 = s0 / kT6Slices;
   const long long ntiles = (s1 - s0 + kT6Slices - 1) / kT6Slices;
   auto kernel = tile6::sym_spmv_tile_kernel<T, HALO, DOT>;
-  const int smem = m->t6_smem_entries * (int)sizeof(T);
+  // products of the largest tile (rounded to 8 entries) + its slot offsets
+  const int prod_entries = (m->t6_smem_entries + 7) & ~7;
+  const int smem = prod_entries * (int)sizeof(T) + (m->t6_max_cols + 2) * 2;
   static int granted = 0; // per instantiation
   if (granted < smem) {
+    const int cap = kT6MaxSmemBytes + (kT6MaxCols + 2) * 2;
     CFS_CUDA_TRY(cudaFuncSetAttribute(
-        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT6MaxSmemBytes));
-    granted = kT6MaxSmemBytes;
+        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    granted = cap;
   }
   kernel<<<(unsigned)ntiles, tile6::kThreads, smem, s>>>(
       tile0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->t6_pack.p,
       (const T *)m->sell_val.p, (const T *)m->diagonal.p, m->t6_lo.p,
-      m->t6_ncols.p, m->t6_cptr_off.p, m->t6_cptr.p, xb, yb, y_lower, dot);
+      m->t6_ncols.p, m->t6_cptr_off.p, m->t6_cptr.p, prod_entries, xb, yb,
+      y_lower, dot);
   return CFS_OK;
 }
 

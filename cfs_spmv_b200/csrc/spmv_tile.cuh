@@ -66,14 +66,24 @@ __global__ void __launch_bounds__(kThreads, 2)
                          const int *__restrict__ tile_ncols,
                          const long long *__restrict__ tile_cptr_off,
                          const unsigned short *__restrict__ cptr,
+                         int prod_entries,
                          const T *__restrict__ x, T *__restrict__ y,
                          T *__restrict__ y_lower, double *__restrict__ dot) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *prod = reinterpret_cast<T *>(smem_raw);
+  // the slot offsets of the tile's columns, staged before phase 1 so that
+  // phase 2 does not start with a round trip to global memory
+  unsigned short *cs = reinterpret_cast<unsigned short *>(prod + prod_entries);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = tile_begin + blockIdx.x;
   const long long s = tile * kT6Slices + warp;
   const int lo = tile_lo[tile];
+  const int W = tile_ncols[tile];
+  {
+    const unsigned short *cp = cptr + tile_cptr_off[tile];
+    for (int j = threadIdx.x; j <= W; j += kThreads)
+      cs[j] = cp[j];
+  }
 
   // ---- phase 1: row-major, products to their column-major slots
   if (s < nslices) {
@@ -136,10 +146,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   __syncthreads();
 
   // ---- phase 2: column-major, one coalesced RED per column
-  const int W = tile_ncols[tile];
-  const unsigned short *cp = cptr + tile_cptr_off[tile];
   for (int j = threadIdx.x; j < W; j += kThreads) {
-    const int b = cp[j], e = cp[j + 1];
+    const int b = cs[j], e = cs[j + 1];
     if (e > b) {
       T sum = prod[b];
       for (int k = b + 1; k < e; ++k)

@@ -154,7 +154,7 @@ int build_tiles6(cfs_matrix_s *m, cudaStream_t s) {
   const int max_entries = (int)(kT6MaxSmemBytes / m->vsize());
   std::vector<int> hncols((size_t)nt);
   std::vector<long long> hoff((size_t)nt + 1, 0);
-  int largest = 0;
+  int largest = 0, widest = 0;
   for (long long t = 0; t < nt; ++t) {
     const int W = hcount[t] ? hhi[t] - hlo[t] + 1 : 0;
     if (W > kT6MaxCols - 1 || hcount[t] > max_entries || hcount[t] > 65535)
@@ -162,6 +162,7 @@ int build_tiles6(cfs_matrix_s *m, cudaStream_t s) {
     hncols[t] = W;
     hoff[t + 1] = hoff[t] + W + 1;
     largest = hcount[t] > largest ? hcount[t] : largest;
+    widest = W > widest ? W : widest;
   }
   CFS_TRY(m->t6_lo.alloc((size_t)nt));
   CFS_TRY(m->t6_ncols.alloc((size_t)nt));
@@ -186,6 +187,7 @@ int build_tiles6(cfs_matrix_s *m, cudaStream_t s) {
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
   m->nt6 = nt;
   m->t6_smem_entries = largest;
+  m->t6_max_cols = widest;
   m->t6_cptr_entries = hoff[nt];
   return CFS_OK;
 }
