@@ -118,6 +118,10 @@ bool CSRMatrix<IndexT, ValueT>::ingest_on_gpu(const string &filename,
 #endif
     } else if (status != CFS_ERR_NEEDS_HOST) {
       fatal_unless_ok(status, "cfs_cuda_matrix_create_from_mmf");
+    } else {
+      // never silent: say on stderr why the host loader takes this file (stdout
+      // stays the reference's)
+      fprintf(stderr, "[cfs] %s\n", cfs_cuda_last_error());
     }
   }
   munmap(image, bytes);
