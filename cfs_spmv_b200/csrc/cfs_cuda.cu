@@ -129,6 +129,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.pipeline = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "pipeline_taper") && (value == 0 || value == 1)) {
+    g_options.pipeline_taper = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "pipeline_split") && (value == 0 || value == 1)) {
     g_options.pipeline_split = (int)value;
     return CFS_OK;

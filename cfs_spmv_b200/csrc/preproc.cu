@@ -579,9 +579,23 @@ int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
   auto snap = [&](long long v) { // to a multiple of `unit`
     return (v + unit / 2) / unit * unit;
   };
-  std::vector<long long> cut((size_t)K + 1);
-  for (int c = 0; c <= K; ++c)
-    cut[c] = c == K ? ns : snap(ns * c / K);
+  // pipeline_taper: the first H2D and the last D2H have nothing to overlap
+  // with, so the chunks at both ends are smaller (weights 1, 2, 3, 3, ..., 2, 1)
+  std::vector<long long> weight((size_t)K, 1);
+  if (g_options.pipeline_taper)
+    for (int c = 0; c < K; ++c) {
+      const int edge = c < K - 1 - c ? c : K - 1 - c;
+      weight[c] = edge + 1 < 3 ? edge + 1 : 3;
+    }
+  long long total_weight = 0;
+  for (long long w : weight)
+    total_weight += w;
+  std::vector<long long> cut((size_t)K + 1, 0);
+  long long acc_weight = 0;
+  for (int c = 0; c < K; ++c) {
+    acc_weight += weight[c];
+    cut[c + 1] = c + 1 == K ? ns : snap(ns * acc_weight / total_weight);
+  }
   for (int c = 0; c < K; ++c)
     if (cut[c + 1] <= cut[c])
       return CFS_OK;

@@ -28,22 +28,25 @@ def main():
     x = capi.gen_device_x(1, 0, N, True).cpu().pin_memory()
     y = torch.empty_like(x).pin_memory()
     ref = None
-    for chunks in (4, 6, 8, 12, 16, 24):
-        for split in (0, 1):
-            capi.set_option("pipeline_chunks", chunks)
-            capi.set_option("pipeline_split", split)
-            rp, ci, v = capi.gen_device_csr(spec, is_double=True)
-            A = capi.Matrix(N, N, rp, ci, v, True, True)
-            A.tune(1)
-            del rp, ci, v
-            nnz = A.info()["nnz_full"]
-            ms = timed(A, y, x)
-            if ref is None:
-                ref = y.clone()
-            err = (y - ref).abs().max().item()
-            print("chunks %3d split %d: %.3f ms/step  %.1f GFLOP/s  maxdiff %.1e"
-                  % (chunks, split, ms, 2 * nnz / ms / 1e6, err), flush=True)
-            A.close()
+    for chunks, split, taper in ((6, 1, 0), (6, 1, 1), (8, 1, 0), (8, 1, 1),
+                                 (10, 1, 1), (12, 1, 1), (8, 0, 1)):
+        capi.set_option("pipeline_chunks", chunks)
+        capi.set_option("pipeline_split", split)
+        capi.set_option("pipeline_taper", taper)
+        rp, ci, v = capi.gen_device_csr(spec, is_double=True)
+        A = capi.Matrix(N, N, rp, ci, v, True, True)
+        A.tune(1)
+        del rp, ci, v
+        nnz = A.info()["nnz_full"]
+        ms = timed(A, y, x)
+        if ref is None:
+            ref = y.clone()
+        err = (y - ref).abs().max().item()
+        print("chunks %3d split %d taper %d: %.3f ms/step  %.1f GFLOP/s  "
+              "maxdiff %.1e" % (chunks, split, taper, ms, 2 * nnz / ms / 1e6,
+                                err), flush=True)
+        A.close()
+    capi.set_option("pipeline_taper", 0)
     capi.set_option("pipeline_chunks", 8)
     capi.set_option("pipeline_split", 1)
     capi.set_option("pipeline_graph", 0)
