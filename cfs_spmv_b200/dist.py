@@ -146,15 +146,43 @@ class P2PHalo:
             peer_x = self.hx.get_buffer(rank - 1, (max_len,), dtype)
             self.x_peer = peer_x[self.h - ph:self.b - ph]
         self.bytes_per_step = 2 * self.nhalo * self.x_sym.element_size()
+        import os
+        self.sync = os.environ.get("CFS_GPU_HALO_SYNC", "barrier")
+
+    # Synchronisation of a step. "barrier": two device barriers over all ranks.
+    # "neighbour" (CFS_GPU_HALO_SYNC=neighbour): the dependencies are only
+    # between adjacent row blocks, so a rank signals / waits for its two
+    # neighbours through the signal pads of the symmetric memory instead:
+    #   before the kernel  r -> r+1 : "my y is clear and my x is final"
+    #   after the kernel   r -> r-1 : "my reductions into your y have landed"
+    _TIMEOUT_MS = 20000
+
+    def sync_before(self):
+        if self.sync != "neighbour":
+            self.hy.barrier()
+            return
+        if self.rank + 1 < self.world:
+            self.hy.put_signal(self.rank + 1, 0, self._TIMEOUT_MS)
+        if self.rank > 0:
+            self.hy.wait_signal(self.rank - 1, 0, self._TIMEOUT_MS)
+
+    def sync_after(self):
+        if self.sync != "neighbour":
+            self.hy.barrier()
+            return
+        if self.rank > 0:
+            self.hy.put_signal(self.rank - 1, 1, self._TIMEOUT_MS)
+        if self.rank + 1 < self.world:
+            self.hy.wait_signal(self.rank + 1, 1, self._TIMEOUT_MS)
 
     def step(self, matrix, stream):
         self.y_ext.zero_()
-        self.hy.barrier()              # every y is clear, every x is final
+        self.sync_before()             # y below is clear, x below is final
         if self.x_peer is not None:
             self.x_ext[:self.nhalo].copy_(self.x_peer)
         matrix.spmv_halo_async(self.y_ext, self.x_ext, self.y_lower_base, True,
                                stream)
-        self.hy.barrier()              # all halo reductions have landed
+        self.sync_after()              # all halo reductions have landed
 
 
 class ShardedSpMV:
@@ -219,8 +247,11 @@ class ShardedSpMV:
             self.exchange_desc = (
                 "fused over NVLink peer memory: x halo pulled from the GPU "
                 "below, y halo contributions reduced by the SpMV kernel straight "
-                "into its y (RED.sys); 2 device barriers per step; %d bytes on "
-                "rank %d" % (self.p2p.bytes_per_step, rank))
+                "into its y (RED.sys); %s per step; %d bytes on "
+                "rank %d" % ("neighbour signals (put / wait) before and after "
+                             "the kernel" if self.p2p.sync == "neighbour"
+                             else "2 device barriers",
+                             self.p2p.bytes_per_step, rank))
         else:
             self.exchange_desc = (
                 "NCCL P2P per step: x halo down-up, y halo strip add; "
@@ -335,13 +366,13 @@ class DistributedCG:
         if op.p2p is not None:
             p2p = op.p2p
             p2p.y_ext.zero_()
-            p2p.hy.barrier()
+            p2p.sync_before()
             if p2p.x_peer is not None:
                 p2p.x_ext[:p2p.nhalo].copy_(p2p.x_peer)
             op.matrix.spmv_halo_dot_async(p2p.y_ext, p2p.x_ext,
                                           p2p.y_lower_base, True,
                                           self.scal[1:2], stream)
-            p2p.hy.barrier()
+            p2p.sync_after()
         else:
             op.y_ext.zero_()
             op.matrix.spmv_halo_dot_async(op.y_ext, op.x_ext, None, True,
