@@ -129,6 +129,10 @@ int cfs_cuda_set_option(const char *key, long long value) {
     g_options.pipeline = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "pipeline_adaptive") && (value == 0 || value == 1)) {
+    g_options.pipeline_adaptive = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "pipeline_taper") && (value == 0 || value == 1)) {
     g_options.pipeline_taper = (int)value;
     return CFS_OK;
@@ -206,6 +210,29 @@ int cfs_cuda_init(int device) {
     return CFS_ERR_NO_DEVICE;
   }
   g_device = device;
+  // CFS_GPU_OPTIONS="key=value,key=value": cfs_cuda_set_option for callers
+  // that only have the environment (the reference's own bench / test binaries)
+  static bool env_options_read = false;
+  if (!env_options_read) {
+    env_options_read = true;
+    if (const char *env = getenv("CFS_GPU_OPTIONS")) {
+      std::string all(env);
+      size_t at = 0;
+      while (at < all.size()) {
+        size_t end = all.find(',', at);
+        if (end == std::string::npos)
+          end = all.size();
+        const std::string item = all.substr(at, end - at);
+        const size_t eq = item.find('=');
+        if (eq != std::string::npos &&
+            cfs_cuda_set_option(item.substr(0, eq).c_str(),
+                                atoll(item.c_str() + eq + 1)) != CFS_OK)
+          fprintf(stderr, "[cfs] CFS_GPU_OPTIONS: ignored '%s'\n",
+                  item.c_str());
+        at = end + 1;
+      }
+    }
+  }
   return CFS_OK;
 }
 

@@ -91,6 +91,7 @@ struct Options {
   int pipeline_chunks = 6;  // row chunks of the pipeline (read at tune time)
   int pipeline_skip = 0;    // measurement aid: 1 no kernels, 2 no D2H, 4 no H2D
   int pipeline_smem = 0;    // dynamic smem of pipelined launches (occupancy cap)
+  int pipeline_adaptive = 1; // fewer chunks for small vectors (>= 4 MB of x each)
   int pipeline_taper = 1;   // smaller chunks at both ends of the pipeline
   int pipeline_split = 1;   // chunks run as head + rest (see build_pipeline_plan)
   int sort_rows = 1; // allow length-sorting of ragged matrices at tune time

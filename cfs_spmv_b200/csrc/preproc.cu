@@ -575,7 +575,13 @@ int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
   CFS_CUDA_TRY(cudaMemcpyAsync(max_row.data(), d_rhi.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
-  const int K = g_options.pipeline_chunks;
+  int K = g_options.pipeline_chunks;
+  if (g_options.pipeline_adaptive) {
+    // every stage costs 10-25 us of hand-overs: keep >= 4 MB of x per chunk
+    const long long by_size =
+        (long long)m->ncols * (long long)m->vsize() / (4ll << 20);
+    K = (int)(by_size < 2 ? 2 : by_size < K ? by_size : K);
+  }
   auto snap = [&](long long v) { // to a multiple of `unit`
     return (v + unit / 2) / unit * unit;
   };

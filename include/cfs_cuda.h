@@ -53,7 +53,9 @@ int cfs_cuda_device_count(int *count);
 int cfs_cuda_init(int device);
 const char *cfs_cuda_last_error(void);
 const char *cfs_cuda_version(void);
-/* run-time tunables; unknown key or bad value: CFS_ERR_INVALID.
+/* run-time tunables; unknown key or bad value: CFS_ERR_INVALID. The
+ * environment variable CFS_GPU_OPTIONS="key=value,key=value" applies the same
+ * settings at cfs_cuda_init (for the reference's own bench / test binaries).
  *   "spmv_variant"   1 = one warp per slice, direct loads; 2 = persistent
  *                    TMA-staged kernel; 4 = shared-memory x/y windows; 5 =
  *                    compressed index stream + shuffle-merged REDs (default; on
@@ -68,7 +70,8 @@ const char *cfs_cuda_version(void);
  *                    of the mean row length, column-wise hub columns
  *   "csr_layout"     0/1  Format::csr streams the sliced layout (default) or
  *                    runs the warp-per-row comparator kernel
- *   "pipeline", "pipeline_chunks", "pipeline_split", "pipeline_graph"
+ *   "pipeline", "pipeline_chunks", "pipeline_adaptive", "pipeline_split",
+ *   "pipeline_taper", "pipeline_graph"
  *                    host-vector path of cfs_cuda_spmv: staged H2D / kernel /
  *                    D2H pipeline, its chunk count, head + rest stages, replay
  *                    as one CUDA graph

@@ -525,7 +525,8 @@ def test_value_indexing_is_lossless(gpu, prec, ndistinct):
 
 
 @pytest.mark.parametrize("kind", ["lap27", "banded"])
-@pytest.mark.parametrize("chunks,split", [(8, 1), (8, 0), (3, 1), (16, 1)])
+@pytest.mark.parametrize("chunks,split", [(8, 1), (8, 0), (3, 1), (16, 1),
+                                          (0, 1)])
 def test_host_vector_pipeline(gpu, chunks, split, kind):
     """cfs_cuda_spmv with HOST x and y on a matrix large enough for the staged
     H2D / kernel / D2H pipeline (>= 4096 slices): pageable vectors (plain
@@ -539,12 +540,15 @@ def test_host_vector_pipeline(gpu, chunks, split, kind):
     rp, ci, v = capi.gen_host_csr(spec)
     n = len(rp) - 1
     o = oracle.Oracle(rp, ci, v, 1)
-    capi.set_option("pipeline_chunks", chunks)
+    # chunks == 0: the default, chunk count adapted to the vector size
+    capi.set_option("pipeline_adaptive", 1 if chunks == 0 else 0)
+    capi.set_option("pipeline_chunks", chunks if chunks else 6)
     capi.set_option("pipeline_split", split)
     try:
         A = capi.Matrix.from_csr(rp, ci, v)
         A.tune(1)
     finally:
+        capi.set_option("pipeline_adaptive", 1)
         capi.set_option("pipeline_chunks", 6)
         capi.set_option("pipeline_split", 1)
     for seed in (1, 2):
