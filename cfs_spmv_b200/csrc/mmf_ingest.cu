@@ -13,8 +13,10 @@
 //                                (decfloat.cuh); lines this parser must not
 //                                decide are listed and patched in from the
 //                                host's strtol / strtod
-//   mirror + order by (row,col)  scan + 64-bit radix sort (stable: duplicates
-//                                stay in file order)
+//   mirror + order by (row,col)  scan + 64-bit radix sort (stable). One
+//                                (row, col) twice with DIFFERENT values: the
+//                                reference's order is std::sort's, the file
+//                                goes to the host loader (same algorithm)
 //   full CSR                     row boundaries of the sorted keys
 //
 // Anything the reference treats as fatal or undefined (short lines, too few
