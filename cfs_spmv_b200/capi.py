@@ -16,6 +16,7 @@ CFS_OK = 0
 CFS_ERR_CUDA, CFS_ERR_INVALID, CFS_ERR_NO_DEVICE, CFS_ERR_STATE, \
     CFS_ERR_TOO_LARGE = 1, 2, 3, 4, 5
 CFS_ERR_NEEDS_HOST = 6
+CFS_ALLOC_DEFAULT, CFS_ALLOC_PLAIN, CFS_ALLOC_PINNED, CFS_ALLOC_MANAGED = 0, 1, 2, 3
 
 META = {
     "row_split": 1, "part_nnz_low": 2, "lower_rowptr": 3, "lower_colind": 4,
@@ -30,6 +31,7 @@ _VALUE_META = ("lower_values", "diagonal", "sell_val")
 DECLARED_SYMBOLS = (
     "cfs_cuda_device_count", "cfs_cuda_init", "cfs_cuda_last_error",
     "cfs_cuda_version", "cfs_cuda_set_option", "cfs_cuda_host_alloc", "cfs_cuda_host_free",
+    "cfs_cuda_host_alloc_kind", "cfs_cuda_vector_prefetch",
     "cfs_cuda_matrix_create", "cfs_cuda_matrix_create_shard",
     "cfs_cuda_matrix_create_from_mmf", "cfs_cuda_matrix_download_csr",
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
@@ -174,6 +176,9 @@ def lib():
     L.cfs_cuda_host_alloc.restype = vp
     L.cfs_cuda_host_alloc.argtypes = [sz]
     L.cfs_cuda_host_free.argtypes = [vp]
+    L.cfs_cuda_host_alloc_kind.restype = vp
+    L.cfs_cuda_host_alloc_kind.argtypes = [sz, ctypes.c_int]
+    L.cfs_cuda_vector_prefetch.argtypes = [vp, sz, ctypes.c_int]
     L.cfs_cuda_matrix_create.argtypes = [ctypes.POINTER(vp), i32, i32, vp, vp,
                                          vp, ctypes.c_int, ctypes.c_int]
     L.cfs_cuda_matrix_create_shard.argtypes = [ctypes.POINTER(vp), i32, i32,

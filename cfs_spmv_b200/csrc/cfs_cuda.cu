@@ -45,11 +45,14 @@ int current_device() { return g_device; }
 
 enum PtrKind { kPtrHost, kPtrDevice };
 
-static int classify(const void *p, PtrKind *kind, bool *pinned = nullptr) {
+static int classify(const void *p, PtrKind *kind, bool *pinned = nullptr,
+                    bool *managed = nullptr) {
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);
   if (pinned)
     *pinned = false;
+  if (managed)
+    *managed = false;
   if (e != cudaSuccess) {
     cudaGetLastError();
     *kind = kPtrHost;
@@ -60,18 +63,29 @@ static int classify(const void *p, PtrKind *kind, bool *pinned = nullptr) {
               : kPtrHost;
   if (pinned)
     *pinned = a.type == cudaMemoryTypeHost;
+  if (managed)
+    *managed = a.type == cudaMemoryTypeManaged;
   return CFS_OK;
 }
 
-// pinned allocations handed out by cfs_cuda_host_alloc (to pick the right free)
+// allocations handed out by cfs_cuda_host_alloc: the kind picks the right free;
+// `seen` marks a managed vector that cfs_cuda_spmv has moved to the GPU once
+struct AllocRec {
+  int kind;
+  size_t bytes;
+  bool seen;
+};
 static std::mutex g_alloc_mutex;
-static std::unordered_map<void *, int> g_allocs; // ptr -> 1 pinned, 0 malloc
+static std::unordered_map<const void *, AllocRec> g_allocs;
 
 static int upload_or_borrow(const void *src, size_t bytes, DevArray<char> &own,
                             const void **out) {
   PtrKind k;
-  CFS_TRY(classify(src, &k));
-  if (k == kPtrDevice) {
+  bool managed = false;
+  CFS_TRY(classify(src, &k, nullptr, &managed));
+  // managed matrix arrays are copied like host arrays: borrowing them would
+  // page-fault them over one 64 KB block at a time
+  if (k == kPtrDevice && !managed) {
     *out = src;
     return CFS_OK;
   }
@@ -90,9 +104,22 @@ extern "C" {
 const char *cfs_cuda_last_error(void) { return g_error; }
 const char *cfs_cuda_version(void) { return "cfs-b200 0.1 (sm_100a)"; }
 
+// bumped by every accepted cfs_cuda_set_option: captured graphs bake the kernel
+// choice in and are re-captured when it has moved on
+static unsigned long long g_options_generation = 1;
+
+static int set_option_checked(const char *key, long long value);
+
 int cfs_cuda_set_option(const char *key, long long value) {
   if (!key)
     return CFS_ERR_INVALID;
+  const int status = set_option_checked(key, value);
+  if (status == CFS_OK)
+    ++g_options_generation;
+  return status;
+}
+
+static int set_option_checked(const char *key, long long value) {
   if (!strcmp(key, "value_index") && (value == 0 || value == 1)) {
     g_options.value_index = (int)value;
     return CFS_OK;
@@ -163,6 +190,14 @@ int cfs_cuda_set_option(const char *key, long long value) {
   }
   if (!strcmp(key, "csr_layout") && (value == 0 || value == 1)) {
     g_options.csr_layout = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "managed_prefetch") && value >= 0 && value <= 2) {
+    g_options.managed_prefetch = (int)value;
+    return CFS_OK;
+  }
+  if (!strcmp(key, "managed_advise") && (value == 0 || value == 1)) {
+    g_options.managed_advise = (int)value;
     return CFS_OK;
   }
   if (!strcmp(key, "cg_batch") && value >= 1 && value <= 4096) {
@@ -236,33 +271,85 @@ int cfs_cuda_init(int device) {
   return CFS_OK;
 }
 
-void *cfs_cuda_host_alloc(size_t bytes) {
-  void *p = nullptr;
+// CFS_GPU_ALLOC=managed|pinned|plain (cfs_cuda.h); read once
+static int default_alloc_kind() {
+  static int kind = 0;
+  if (kind)
+    return kind;
+  kind = CFS_ALLOC_MANAGED;
+  if (const char *env = getenv("CFS_GPU_ALLOC")) {
+    if (!strcmp(env, "pinned"))
+      kind = CFS_ALLOC_PINNED;
+    else if (!strcmp(env, "plain"))
+      kind = CFS_ALLOC_PLAIN;
+    else if (strcmp(env, "managed"))
+      fprintf(stderr, "[cfs] CFS_GPU_ALLOC: unknown kind '%s', using managed\n",
+              env);
+  }
+  return kind;
+}
+
+// The allocator can be the first thing a process calls (bench_spmv_mmf.cpp:127
+// comes before any matrix work in some callers): bind the GPU the process was
+// told to use, not GPU 0, before the first CUDA allocation creates a context.
+static bool bind_for_alloc() {
+  if (g_device >= 0)
+    return cudaSetDevice(g_device) == cudaSuccess;
   int n = 0;
-  if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) {
-    if (g_device >= 0)
-      cudaSetDevice(g_device);
-    if (cudaHostAlloc(&p, bytes ? bytes : 64, cudaHostAllocPortable) ==
-        cudaSuccess) {
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return false;
+  }
+  int dev = 0;
+  if (const char *env = getenv("CFS_GPU_DEVICE")) {
+    const int v = atoi(env);
+    if (v >= 0 && v < n)
+      dev = v;
+  }
+  return cfs_cuda_init(dev) == CFS_OK;
+}
+
+void *cfs_cuda_host_alloc_kind(size_t bytes, int kind) {
+  void *p = nullptr;
+  if (kind == CFS_ALLOC_DEFAULT)
+    kind = default_alloc_kind();
+  const size_t want = bytes ? bytes : 64;
+  if (kind != CFS_ALLOC_PLAIN && bind_for_alloc()) {
+    if (kind == CFS_ALLOC_MANAGED) {
+      if (cudaMallocManaged(&p, want, cudaMemAttachGlobal) == cudaSuccess) {
+        // the vectors belong in HBM whenever the GPU works on them
+        if (g_options.managed_advise)
+          cudaMemAdvise(p, want, cudaMemAdviseSetPreferredLocation, g_device);
+        cudaGetLastError();
+        std::lock_guard<std::mutex> hold(g_alloc_mutex);
+        g_allocs[p] = AllocRec{CFS_ALLOC_MANAGED, want, false};
+        return p;
+      }
+    } else if (cudaHostAlloc(&p, want, cudaHostAllocPortable) == cudaSuccess) {
       std::lock_guard<std::mutex> hold(g_alloc_mutex);
-      g_allocs[p] = 1;
+      g_allocs[p] = AllocRec{CFS_ALLOC_PINNED, want, false};
       return p;
     }
   }
   cudaGetLastError();
-  // host-only bookkeeping (MMF loading on a box without a GPU): plain 64-byte
-  // aligned memory, exactly what the reference returns (allocator.cpp:33)
-  if (posix_memalign(&p, 64, bytes ? bytes : 64) != 0)
+  // no GPU (MMF loading on a host-only box) or arrays that are uploaded once:
+  // plain 64-byte aligned memory, exactly what the reference returns
+  // (allocator.cpp:33)
+  if (posix_memalign(&p, 64, want) != 0)
     return nullptr;
   std::lock_guard<std::mutex> hold(g_alloc_mutex);
-  g_allocs[p] = 0;
+  g_allocs[p] = AllocRec{CFS_ALLOC_PLAIN, want, false};
   return p;
+}
+
+void *cfs_cuda_host_alloc(size_t bytes) {
+  return cfs_cuda_host_alloc_kind(bytes, CFS_ALLOC_DEFAULT);
 }
 
 void cfs_cuda_host_free(void *ptr) {
   if (!ptr)
     return;
-  int kind = 0;
+  int kind = CFS_ALLOC_PLAIN;
   {
     std::lock_guard<std::mutex> hold(g_alloc_mutex);
     auto it = g_allocs.find(ptr);
@@ -270,13 +357,36 @@ void cfs_cuda_host_free(void *ptr) {
       free(ptr); // not ours: behave like the reference's free()
       return;
     }
-    kind = it->second;
+    kind = it->second.kind;
     g_allocs.erase(it);
   }
-  if (kind == 1)
+  if (kind == CFS_ALLOC_PINNED)
     cudaFreeHost(ptr);
+  else if (kind == CFS_ALLOC_MANAGED)
+    cudaFree(ptr);
   else
     free(ptr);
+}
+
+int cfs_cuda_vector_prefetch(const void *ptr, size_t bytes, int to_device) {
+  if (!ptr)
+    return CFS_ERR_INVALID;
+  PtrKind k;
+  bool managed = false;
+  classify(ptr, &k, nullptr, &managed);
+  if (!managed || bytes == 0)
+    return CFS_OK;
+  CFS_TRY(require_device());
+  CFS_CUDA_TRY(cudaMemPrefetchAsync(ptr, bytes,
+                                    to_device ? g_device : cudaCpuDeviceId, 0));
+  CFS_CUDA_TRY(cudaStreamSynchronize(0));
+  if (!to_device) {
+    std::lock_guard<std::mutex> hold(g_alloc_mutex);
+    auto it = g_allocs.find(ptr);
+    if (it != g_allocs.end())
+      it->second.seen = false;
+  }
+  return CFS_OK;
 }
 
 static int create_common(cfs_mat_t *out, int32_t nrows, int32_t ncols,
@@ -303,7 +413,10 @@ static int create_common(cfs_mat_t *out, int32_t nrows, int32_t ncols,
     DevArray<char> tmp;
     const void *p = nullptr;
     PtrKind k;
-    classify(rowptr, &k);
+    bool managed = false;
+    classify(rowptr, &k, nullptr, &managed);
+    if (managed) // copied like a host array (see upload_or_borrow)
+      k = kPtrHost;
     int32_t nnz = 0;
     if (k == kPtrDevice) {
       if (cudaMemcpy(&nnz, rowptr + nrows, 4, cudaMemcpyDeviceToHost) !=
@@ -330,7 +443,9 @@ static int create_common(cfs_mat_t *out, int32_t nrows, int32_t ncols,
       status = CFS_ERR_INVALID;
       break;
     }
-    classify(colind, &k);
+    classify(colind, &k, nullptr, &managed);
+    if (managed)
+      k = kPtrHost;
     if (k == kPtrDevice || nnz == 0) {
       m->csr_colind = colind;
     } else {
@@ -694,7 +809,8 @@ static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x,
   if (!m->stage_y.p)
     CFS_TRY(m->stage_y.alloc((size_t)m->nrows * vs));
   if (pinned && g_options.pipeline_graph) {
-    if (!m->pipe_graph || m->pipe_x != x || m->pipe_y != y) {
+    if (!m->pipe_graph || m->pipe_x != x || m->pipe_y != y ||
+        m->pipe_generation != g_options_generation) {
       if (m->pipe_graph) {
         cudaGraphExecDestroy(m->pipe_graph);
         m->pipe_graph = nullptr;
@@ -715,6 +831,7 @@ static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x,
       CFS_CUDA_TRY(ei);
       m->pipe_x = x;
       m->pipe_y = y;
+      m->pipe_generation = g_options_generation;
     }
     CFS_CUDA_TRY(cudaGraphLaunch(m->pipe_graph, m->stream));
     CFS_CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -739,6 +856,45 @@ static int spmv_host_pipelined(cfs_mat_t m, void *y, const void *x,
   return CFS_OK;
 }
 
+// Unified-memory vectors (cfs_cuda_host_alloc, kind managed): the kernel runs
+// straight on them. A vector the host has just written sits in host pages; one
+// bulk prefetch moves it 3x faster than a page fault per 64 KB block, but a
+// prefetch of pages that are resident already costs 55-95 us (measured,
+// tools/managed_probe.cu) -- more than the whole SpMV of BASELINE configs[0].
+// Policy (option managed_prefetch):
+//   0 = never;
+//   1 = (default) when this library has not yet brought the allocation to the
+//       GPU, and for a while after a call that evidently ran into page faults
+//       (see cfs_cuda_spmv): the host loop of the reference never touches the
+//       vectors between calls (bench_spmv_mmf.cpp:162-167) and pays nothing, a
+//       caller that rewrites x between calls gets bulk transfers;
+//   2 = on every call.
+// Correct in all three: pages the host touched come over by GPU page faults.
+static int managed_to_device(const void *p, size_t bytes, cudaStream_t s,
+                             bool force, bool *moved) {
+  const int mode = g_options.managed_prefetch;
+  if (mode == 0 || bytes == 0)
+    return CFS_OK;
+  if (mode == 1) {
+    std::lock_guard<std::mutex> hold(g_alloc_mutex);
+    auto it = g_allocs.find(p);
+    if (it != g_allocs.end()) {
+      if (it->second.seen && !force)
+        return CFS_OK;
+      it->second.seen = true;
+    }
+  }
+  CFS_CUDA_TRY(cudaMemPrefetchAsync(p, bytes, g_device, s));
+  *moved = true;
+  return CFS_OK;
+}
+
+static double wall_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
 int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   if (!m || !y || !x)
     return CFS_ERR_INVALID;
@@ -753,12 +909,23 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
                           : (size_t)m->ncols;
   const size_t ylen = m->sharded ? xlen : (size_t)m->nrows;
   PtrKind kx, ky;
-  bool px = false, py = false;
-  classify(x, &kx, &px);
-  classify(y, &ky, &py);
+  bool px = false, py = false, mx = false, my = false;
+  classify(x, &kx, &px, &mx);
+  classify(y, &ky, &py, &my);
   if (kx == kPtrHost && ky == kPtrHost && m->symmetric && !m->stages.empty() &&
       g_options.pipeline)
     return spmv_host_pipelined(m, y, x, px && py);
+  // a call on unified memory that took far longer than the matrix can explain
+  // ran into page faults: the host touches the vectors between calls, so the
+  // next `managed_hot` calls prefetch; when they are used up one call goes
+  // without, and if that faults again the window doubles
+  const bool hot = m->managed_hot > 0;
+  const double t_call = (mx || my) ? wall_us() : 0.0;
+  bool prefetched = false;
+  if (mx)
+    CFS_TRY(managed_to_device(x, xlen * vs, m->stream, hot, &prefetched));
+  if (my)
+    CFS_TRY(managed_to_device(y, ylen * vs, m->stream, hot, &prefetched));
   const void *xd = x;
   void *yd = y;
   if (kx == kPtrHost) {
@@ -778,6 +945,25 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
     CFS_CUDA_TRY(cudaMemcpyAsync(y, yd, ylen * vs, cudaMemcpyDeviceToHost,
                                  m->stream));
   CFS_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if ((mx || my) && g_options.managed_prefetch == 1) {
+    if (hot) {
+      --m->managed_hot;
+    } else if (!prefetched) {
+      // generous bound for a fault-free call: the algorithmic bytes at a
+      // quarter of a slow kernel's rate plus launch and wake-up latency
+      cfs_matrix_info info;
+      cfs_cuda_matrix_info(m, &info);
+      const double expect_us = 100.0 + 4.0 * (double)info.algorithmic_bytes / 3e6;
+      if (wall_us() - t_call > expect_us) {
+        m->managed_window = m->managed_window ? 2 * m->managed_window : 8;
+        if (m->managed_window > 4096)
+          m->managed_window = 4096;
+        m->managed_hot = m->managed_window;
+      } else {
+        m->managed_window = 0;
+      }
+    }
+  }
   return CFS_OK;
 }
 

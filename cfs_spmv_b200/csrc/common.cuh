@@ -100,6 +100,8 @@ struct Options {
   int rechunk_pct = 130; // ... as a percentage of the mean row length
   int rechunk = 1;     // ragged matrices: virtual rows of ~1.3 x the mean row length
   int tile6 = 1;      // variant 6 where it applies (bounded column windows)
+  int managed_prefetch = 1; // managed vectors: 0 never, 1 first use, 2 every call
+  int managed_advise = 1;   // managed vectors: preferred location = the GPU
   int cg_batch = 16; // CG iterations enqueued between two looks at the stop flag
   int diag_mode = 0; // measurement aid, see spmv.cu (non-zero: wrong results)
 };
@@ -202,6 +204,9 @@ struct cfs_matrix_s {
   // staging for the synchronous host-pointer entry point
   cfsb::DevArray<char> stage_x, stage_y;
   cudaStream_t stream = nullptr;
+  // unified-memory vectors (cfs_cuda_spmv): calls that still prefetch after a
+  // call that ran into page faults, and the size of that window
+  int managed_hot = 0, managed_window = 0;
   // Host-vector pipeline (cfs_cuda_spmv with host x and y): the lower triangle
   // only looks DOWN, so a chunk of rows can run as soon as x up to its last row
   // has arrived, and its y rows are final once every chunk that reaches down
@@ -221,6 +226,7 @@ struct cfs_matrix_s {
   cudaGraphExec_t pipe_graph = nullptr; // the step captured for (pipe_x, pipe_y)
   const void *pipe_x = nullptr;
   void *pipe_y = nullptr;
+  unsigned long long pipe_generation = 0; // options generation of the capture
 };
 
 namespace cfsb {

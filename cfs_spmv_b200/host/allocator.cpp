@@ -20,6 +20,15 @@ void *internal_alloc(size_t bytes, Platform) {
   return p;
 }
 
+void *internal_alloc_host(size_t bytes) {
+  void *p = cfs_cuda_host_alloc_kind(bytes, CFS_ALLOC_PLAIN);
+  if (!p) {
+    std::cout << "[ERROR]: cfs_cuda_host_alloc_kind() failed!" << std::endl;
+    exit(1);
+  }
+  return p;
+}
+
 void internal_free(void *pointer, Platform) { cfs_cuda_host_free(pointer); }
 
 } // namespace memory

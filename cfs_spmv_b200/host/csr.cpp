@@ -134,10 +134,10 @@ void CSRMatrix<IndexT, ValueT>::fetch_host_csr() const {
   if (!host_csr_pending_)
     return;
   host_csr_pending_ = false;
-  rowptr_ = (IndexT *)internal_alloc(((size_t)nrows_ + 1) * sizeof(IndexT),
-                                     platform_);
-  colind_ = (IndexT *)internal_alloc((size_t)nnz_ * sizeof(IndexT), platform_);
-  values_ = (ValueT *)internal_alloc((size_t)nnz_ * sizeof(ValueT), platform_);
+  // uploaded once: plain host memory, not the vectors' unified memory
+  rowptr_ = (IndexT *)internal_alloc_host(((size_t)nrows_ + 1) * sizeof(IndexT));
+  colind_ = (IndexT *)internal_alloc_host((size_t)nnz_ * sizeof(IndexT));
+  values_ = (ValueT *)internal_alloc_host((size_t)nnz_ * sizeof(ValueT));
   fatal_unless_ok(cfs_cuda_matrix_download_csr(device_, (int32_t *)rowptr_,
                                                (int32_t *)colind_, values_),
                   "cfs_cuda_matrix_download_csr");
@@ -180,10 +180,10 @@ CSRMatrix<IndexT, ValueT>::CSRMatrix(const string &filename, Platform platform,
   nrows_ = mmf.GetNrRows();
   ncols_ = mmf.GetNrCols();
   nnz_ = mmf.GetNrNonzeros();
-  rowptr_ = (IndexT *)internal_alloc(((size_t)nrows_ + 1) * sizeof(IndexT),
-                                     platform_);
-  colind_ = (IndexT *)internal_alloc((size_t)nnz_ * sizeof(IndexT), platform_);
-  values_ = (ValueT *)internal_alloc((size_t)nnz_ * sizeof(ValueT), platform_);
+  // uploaded once: plain host memory, not the vectors' unified memory
+  rowptr_ = (IndexT *)internal_alloc_host(((size_t)nrows_ + 1) * sizeof(IndexT));
+  colind_ = (IndexT *)internal_alloc_host((size_t)nnz_ * sizeof(IndexT));
+  values_ = (ValueT *)internal_alloc_host((size_t)nnz_ * sizeof(ValueT));
 
   // counting pass, then a running sum: rows without entries repeat rowptr
   for (IndexT i = 0; i <= nrows_; ++i)

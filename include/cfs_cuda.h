@@ -85,11 +85,37 @@ int cfs_cuda_set_option(const char *key, long long value);
 
 /* ---- allocator: backs internal_alloc / internal_free
  * (include/utils/allocator.hpp:11-12, src/allocator.cpp:8-43).
- * 64-byte aligned like the reference; page-locked when a GPU is present so the
- * host vectors the bench/test allocate are DMA-able. Returns NULL on failure
- * (the C++ wrapper prints and exit(1)s like the reference). */
+ * 64-byte aligned like the reference. The reference's bench / test take x and y
+ * from internal_alloc, fill x on the host, call y = A x in a loop that never
+ * looks at the vectors (bench_spmv_mmf.cpp:154-167) and read y on the host
+ * afterwards (test_spmv_mmf.cpp:94-104). So that such a caller runs at kernel
+ * speed the default kind is UNIFIED (managed) memory: cfs_cuda_spmv launches
+ * straight on it, the vectors live in HBM while the GPU works on them and come
+ * back page by page when the host touches them. Kinds:
+ *   CFS_ALLOC_MANAGED  cudaMallocManaged, preferred location = the process's GPU
+ *   CFS_ALLOC_PINNED   page-locked host memory: cfs_cuda_spmv copies x in and y
+ *                      out on every call (pipelined)
+ *   CFS_ALLOC_PLAIN    posix_memalign (what the reference returns); the choice
+ *                      for arrays that are uploaded once (the CSR of the host
+ *                      loader)
+ *   CFS_ALLOC_DEFAULT  the environment's CFS_GPU_ALLOC=managed|pinned|plain, else
+ *                      managed; plain when no GPU is visible
+ * cfs_cuda_host_alloc(bytes) = cfs_cuda_host_alloc_kind(bytes, CFS_ALLOC_DEFAULT).
+ * Returns NULL on failure (the C++ wrapper prints and exit(1)s like the
+ * reference). cfs_cuda_host_free takes any of them (and, like the reference's
+ * free(), pointers it has never seen). */
+#define CFS_ALLOC_DEFAULT 0
+#define CFS_ALLOC_PLAIN 1
+#define CFS_ALLOC_PINNED 2
+#define CFS_ALLOC_MANAGED 3
 void *cfs_cuda_host_alloc(size_t bytes);
+void *cfs_cuda_host_alloc_kind(size_t bytes, int kind);
 void cfs_cuda_host_free(void *ptr);
+/* Where a vector should be before its next use, for callers that know (optional;
+ * correctness never depends on it): to_device != 0 moves a managed range to the
+ * GPU, 0 brings it to the host, in one bulk transfer instead of page faults.
+ * No-op for the other kinds. */
+int cfs_cuda_vector_prefetch(const void *ptr, size_t bytes, int to_device);
 
 /* ---- matrix construction: replaces CSRMatrix(rowptr, colind, values, nrows,
  * ncols, symmetric, ...) (include/matrix/csr_matrix.tpp:114-144) and is what

@@ -74,6 +74,21 @@ template <typename V> static int run(const string &file, Format fmt) {
   bool ok = same(y, y_csr, M) && A->nnz() == C->nnz() && A->size() > 0;
   cout << "file ctor: " << (ok ? "PASSED!" : "FAILED!") << endl;
   failures += !ok;
+  // 1b. the host rewrites x between two calls and reads y after each (the
+  // vectors come from internal_alloc: unified memory by default, so this is
+  // the page-migration path in both directions)
+  for (int i = 0; i < N; ++i)
+    x[i] *= (V)2;
+  fn(y, M, x, N);
+  for (int i = 0; i < M; ++i)
+    y[i] *= (V)0.5;
+  ok = same(y, y_csr, M);
+  for (int i = 0; i < N; ++i)
+    x[i] *= (V)0.5;
+  fn(y, M, x, N);
+  ok = ok && same(y, y_csr, M);
+  cout << "host-mutated x: " << (ok ? "PASSED!" : "FAILED!") << endl;
+  failures += !ok;
   // a symmetric file matrix gives its full CSR back during tune()
   if (was_symmetric) {
     CSRMatrix<int, V> *Ac = static_cast<CSRMatrix<int, V> *>(A);
