@@ -36,6 +36,7 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_matrix_create_from_mmf", "cfs_cuda_matrix_download_csr",
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
     "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_halo_async",
+    "cfs_cuda_spmv_shard_async",
     "cfs_cuda_spmv_timed", "cfs_cuda_cg_solve",
     "cfs_cuda_spmv_halo_dot_async", "cfs_cuda_cg_update_xr",
     "cfs_cuda_cg_update_p",
@@ -59,10 +60,11 @@ class GenSpec(ctypes.Structure):
                 ("per_row", ctypes.c_int32), ("seed", ctypes.c_uint64)]
 
     @staticmethod
-    def laplacian(points, nx, ny, nz):
+    def laplacian(points, nx, ny, nz, seed=0):
+        """seed != 0: one coefficient per edge (cfs_gen.h) instead of -1"""
         assert points in (7, 27)
         return GenSpec(1 if points == 7 else 2, nx, ny, nz, nx * ny * nz, 0, 0,
-                       0)
+                       seed)
 
     @staticmethod
     def banded(nrows, bw, per_row_x16, seed):
@@ -71,8 +73,9 @@ class GenSpec(ctypes.Structure):
     def ref_tool_spec(self):
         """the same matrix, spelled for oracle/_ref/ref_tool"""
         if self.kind in (1, 2):
-            return "gen:lap%d:%d:%d:%d" % (7 if self.kind == 1 else 27,
-                                           self.nx, self.ny, self.nz)
+            return "gen:lap%d:%d:%d:%d%s" % (
+                7 if self.kind == 1 else 27, self.nx, self.ny, self.nz,
+                ":%d" % self.seed if self.seed else "")
         return "gen:banded:%d:%d:%d:%d" % (self.nrows, self.bw, self.per_row,
                                            self.seed)
 
@@ -194,6 +197,8 @@ def lib():
     L.cfs_cuda_spmv.argtypes = [vp, vp, vp]
     L.cfs_cuda_spmv_async.argtypes = [vp, vp, vp, vp]
     L.cfs_cuda_spmv_halo_async.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
+    L.cfs_cuda_spmv_shard_async.argtypes = [vp, vp, vp, vp, vp, vp,
+                                            ctypes.c_int, vp]
     L.cfs_cuda_spmv_timed.argtypes = [vp, vp, vp, vp, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_float),
                                       ctypes.POINTER(ctypes.c_float)]
@@ -338,6 +343,15 @@ class Matrix:
         check(lib().cfs_cuda_spmv_halo_async(self._h, _ptr(y_dev), _ptr(x_dev),
                                              y_lower_base, int(y_is_zero),
                                              stream))
+
+    def spmv_shard_async(self, y_dev, x_dev, y_lower_base=None,
+                         x_lower_base=None, y_clear=None, y_is_zero=True,
+                         stream=0):
+        """spmv_halo_async that reads the x halo from the GPU below and clears
+        the owned rows of y_clear for the next SpMV (ping-pong results)"""
+        check(lib().cfs_cuda_spmv_shard_async(
+            self._h, _ptr(y_dev), _ptr(x_dev), y_lower_base, x_lower_base,
+            _ptr(y_clear), int(y_is_zero), stream))
 
     def cg_solve(self, x, b, max_iters, rel_tol, want_history=False):
         """A x = b by conjugate gradients on the device (cfs_cuda_cg_solve).

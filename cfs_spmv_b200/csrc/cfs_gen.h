@@ -30,7 +30,11 @@ typedef struct cfs_gen_spec {
   int64_t nrows;      /* number of rows (= nx*ny*nz for the Laplacians)      */
   int32_t bw;         /* BANDED: half bandwidth                              */
   int32_t per_row;    /* BANDED: expected lower entries per row, times 16    */
-  uint64_t seed;      /* BANDED: pattern/value seed                          */
+  uint64_t seed;      /* BANDED: pattern/value seed. Laplacians: 0 = the
+                         constant-coefficient stencil (off-diagonals -1); else
+                         every edge {i,j} gets its own coefficient in
+                         [-1, -0.5) (a heterogeneous diffusion problem: ~nnz/2
+                         distinct values) and the diagonal is 1/16 + sum |a|  */
 } cfs_gen_spec;
 
 /* splitmix64 finaliser: the only random source used anywhere */
@@ -88,6 +92,8 @@ CFS_GEN_FN int cfs_gen_row(const cfs_gen_spec *g, int64_t row, int32_t *cols,
     const int y = (int)((row / nx) % ny);
     const int z = (int)(row / (nx * ny));
     const int full = (g->kind == CFS_GEN_LAP27);
+    double absum = 0.0;
+    int diag_at = -1;
     for (int dz = -1; dz <= 1; ++dz) {
       if (z + dz < 0 || z + dz >= nz)
         continue;
@@ -101,13 +107,26 @@ CFS_GEN_FN int cfs_gen_row(const cfs_gen_spec *g, int64_t row, int32_t *cols,
           if (!full && manhattan > 1)
             continue;
           if (cols) {
-            cols[n] = (int32_t)(row + dx + nx * (dy + ny * (int64_t)dz));
-            vals[n] = manhattan == 0 ? (full ? 26.0 : 6.0) : -1.0;
+            const int64_t col = row + dx + nx * (dy + ny * (int64_t)dz);
+            cols[n] = (int32_t)col;
+            if (g->seed == 0) {
+              vals[n] = manhattan == 0 ? (full ? 26.0 : 6.0) : -1.0;
+            } else if (manhattan == 0) {
+              diag_at = n;
+            } else {
+              const uint64_t lo = (uint64_t)(col < row ? col : row);
+              const uint64_t hi = (uint64_t)(col < row ? row : col);
+              const double a = 0.5 + 0.5 * cfs_u01(cfs_hash3(g->seed, lo, hi));
+              vals[n] = -a;
+              absum += a; /* ascending columns: one order everywhere */
+            }
           }
           ++n;
         }
       }
     }
+    if (cols && diag_at >= 0)
+      vals[diag_at] = 0.0625 + absum;
     return n;
   }
   /* BANDED */
@@ -149,7 +168,13 @@ CFS_GEN_FN int cfs_gen_row(const cfs_gen_spec *g, int64_t row, int32_t *cols,
 }
 
 /* spec constructors */
+CFS_GEN_FN cfs_gen_spec cfs_gen_laplacian_seeded(int points, int nx, int ny,
+                                                 int nz, uint64_t seed);
 CFS_GEN_FN cfs_gen_spec cfs_gen_laplacian(int points, int nx, int ny, int nz) {
+  return cfs_gen_laplacian_seeded(points, nx, ny, nz, 0);
+}
+CFS_GEN_FN cfs_gen_spec cfs_gen_laplacian_seeded(int points, int nx, int ny,
+                                                 int nz, uint64_t seed) {
   cfs_gen_spec g;
   g.kind = points == 7 ? CFS_GEN_LAP7 : CFS_GEN_LAP27;
   g.nx = nx;
@@ -158,7 +183,7 @@ CFS_GEN_FN cfs_gen_spec cfs_gen_laplacian(int points, int nx, int ny, int nz) {
   g.nrows = (int64_t)nx * ny * nz;
   g.bw = 0;
   g.per_row = 0;
-  g.seed = 0;
+  g.seed = seed;
   return g;
 }
 

@@ -100,6 +100,8 @@ struct Options {
   int rechunk_pct = 130; // ... as a percentage of the mean row length
   int rechunk = 1;     // ragged matrices: virtual rows of ~1.3 x the mean row length
   int tile6 = 1;      // variant 6 where it applies (bounded column windows)
+  int reg_blocks = 16; // variant 5: resident 128-thread CTAs per SM asked for (16 or 12)
+  int l2_prefetch = 1; // variant 5, streamed values: prefetch.global.L2 per slice
   int managed_prefetch = 1; // managed vectors: 0 never, 1 first use, 2 every call
   int managed_advise = 1;   // managed vectors: preferred location = the GPU
   int cg_batch = 16; // CG iterations enqueued between two looks at the stop flag
@@ -156,6 +158,7 @@ struct cfs_matrix_s {
 
   // execution layout: sliced ELL over virtual rows
   int64_t nvrows = 0, nslices = 0, padded_entries = 0;
+  int max_slice_steps = 0; // widest slice (steps of 32 entries)
   int64_t sort_window = 0; // 0: natural order; else rows sorted by length in windows
   cfsb::DevArray<int32_t> slice_ptr;  // nslices+1, units of 32 entries
   cfsb::DevArray<int32_t> vrow_row;   // nslices*32
@@ -260,13 +263,18 @@ int build_refmeta(cfs_matrix_s *m, cudaStream_t s);
 // ev0/ev1 (optional) are recorded directly before/after the kernel launch
 // y_lower_base: virtual base of the y vector of the GPU below (fused halo
 // reduction over NVLink) or nullptr; y_is_zero: the caller cleared y already;
+// x_lower_base: virtual base of the x vector of the GPU below (halo entries of
+// x are then read from there instead of the local halo part); y_clear: a
+// vector like y_ext whose OWNED rows the kernel clears (ping-pong results)
 // xdoty: kDotSlots partial sums (stride kDotStride doubles) that the kernel
 // adds x'(A x) into (the caller zeroes them), or nullptr
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     cudaStream_t s, cudaEvent_t ev0 = nullptr,
                     cudaEvent_t ev1 = nullptr, void *y_lower_base = nullptr,
                     bool y_is_zero = false, long long slice0 = 0,
-                    long long slice1 = -1, double *xdoty = nullptr);
+                    long long slice1 = -1, double *xdoty = nullptr,
+                    const void *x_lower_base = nullptr,
+                    void *y_clear = nullptr);
 // host-vector pipeline plan (preproc.cu)
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,

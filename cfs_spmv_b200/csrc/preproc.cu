@@ -457,6 +457,22 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
     m->sort_window = window;
   }
   m->padded_entries = (int64_t)total_width * kSliceRows;
+  // widest slice: the stride of a warp's shared-memory piece in variant 7
+  m->max_slice_steps = 0;
+  if (m->nslices > 0) {
+    DevArray<int> wmax;
+    CFS_TRY(wmax.alloc(1));
+    size_t tb = 0;
+    CFS_CUDA_TRY(cub::DeviceReduce::Max(nullptr, tb, width.p, wmax.p,
+                                        (int)m->nslices, s));
+    DevArray<char> tmp;
+    CFS_TRY(tmp.alloc(tb));
+    CFS_CUDA_TRY(cub::DeviceReduce::Max(tmp.p, tb, width.p, wmax.p,
+                                        (int)m->nslices, s));
+    CFS_CUDA_TRY(cudaMemcpyAsync(&m->max_slice_steps, wmax.p, 4,
+                                 cudaMemcpyDeviceToHost, s));
+    CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  }
   CFS_TRY(m->sell_col.alloc((size_t)m->padded_entries));
   CFS_TRY(m->sell_val.alloc((size_t)m->padded_entries * m->vsize()));
   if (m->nslices > 0) {

@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(kSpmvThreads)
                          const T *__restrict__ sell_val,
                          const T *__restrict__ diagonal,
                          const T *__restrict__ x, T *__restrict__ y,
-                         T *__restrict__ y_lower, double *__restrict__ dot) {
+                         T *__restrict__ y_lower, double *__restrict__ dot,
+                         const T *__restrict__ x_lower,
+                         T *__restrict__ y_clear) {
   const int lane = threadIdx.x & 31;
   const long long s =
       slice_begin + ((blockIdx.x * (long long)kSpmvThreads + threadIdx.x) >> 5);
@@ -109,7 +111,10 @@ __global__ void __launch_bounds__(kSpmvThreads)
       hub[u] = HUBS && c[u] >= 0 && (c[u] & kHubFlag);
       if (HUBS && c[u] >= 0)
         c[u] &= ~kHubFlag;
-      xc[u] = c[u] >= 0 ? ((MODE & 2) ? xr : x[c[u]]) : T(0);
+      xc[u] = c[u] >= 0 ? ((MODE & 2) ? xr
+                                      : tma::x_at<HALO>(x, x_lower, row_begin,
+                                                        c[u]))
+                        : T(0);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -131,15 +136,19 @@ __global__ void __launch_bounds__(kSpmvThreads)
       const bool hub = HUBS && (c & kHubFlag);
       if (HUBS)
         c &= ~kHubFlag;
-      acc += a * ((MODE & 2) ? xr : x[c]);
+      acc += a * ((MODE & 2) ? xr
+                             : tma::x_at<HALO>(x, x_lower, row_begin, c));
       if (!(MODE & 1) && !hub)
         tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
     }
     cp += kSliceRows;
     vp += kSliceRows;
   }
-  if (active)
+  if (active) {
     tma::red_add(y + row, acc);
+    if (y_clear && !(tag & kVrowCont)) // see spmv_reg.cuh
+      y_clear[row] = T(0);
+  }
   if (DOT) { // x'(A x), see spmv_reg.cuh
     double c = (double)xr * (2.0 * (double)acc - (double)dterm);
 #pragma unroll
@@ -175,48 +184,44 @@ __global__ void __launch_bounds__(kSpmvThreads)
 
 constexpr int kStages = 2; // ring depth of the persistent kernel
 
+// what only the sharded / ping-pong entry points set: the x vector of the GPU
+// below (virtual base, read over NVLink by the halo kernels) and the vector the
+// row owners clear for the next SpMV
+struct Extras {
+  const void *x_lower = nullptr;
+  void *y_clear = nullptr;
+};
+
 template <typename T, int MODE>
 void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-                 cudaStream_t s, long long s0, long long s1,
+                 cudaStream_t s, long long s0, long long s1, const Extras &ex,
                  double *dot = nullptr) {
   const unsigned grid =
       (unsigned)(((s1 - s0) * 32 + kSpmvThreads - 1) / kSpmvThreads);
   // hub columns: flagged column stream + a second, column-wise kernel
   const bool hubs = MODE == 0 && !y_lower && m->nhubs > 0 && g_options.hubs &&
                     s0 == 0 && s1 == m->nslices;
+  const T *xl = ex.x_lower ? (const T *)ex.x_lower : xb;
+  T *yc = (T *)ex.y_clear;
+#define CFS_LAUNCH_SELL(M, HALO, HUBS, DOT, COLS, YL, DOTP)                    \
+  sym_spmv_sell_kernel<T, M, HALO, HUBS, DOT><<<grid, kSpmvThreads, 0, s>>>(   \
+      s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, COLS,               \
+      (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, YL, DOTP,    \
+      xl, yc)
   if (y_lower && dot)
-    sym_spmv_sell_kernel<T, 0, true, false, true>
-        <<<grid, kSpmvThreads, 0, s>>>(
-            s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
-            (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower,
-            dot);
+    CFS_LAUNCH_SELL(0, true, false, true, m->sell_col.p, y_lower, dot);
   else if (y_lower)
-    sym_spmv_sell_kernel<T, MODE, true, false><<<grid, kSpmvThreads, 0, s>>>(
-        s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
-        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, y_lower,
-        nullptr);
+    CFS_LAUNCH_SELL(MODE, true, false, false, m->sell_col.p, y_lower, nullptr);
   else if (hubs && dot)
-    sym_spmv_sell_kernel<T, 0, false, true, true>
-        <<<grid, kSpmvThreads, 0, s>>>(
-            s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p,
-            m->hub_colstream.p, (const T *)m->sell_val.p,
-            (const T *)m->diagonal.p, xb, yb, nullptr, dot);
+    CFS_LAUNCH_SELL(0, false, true, true, m->hub_colstream.p, nullptr, dot);
   else if (hubs)
-    sym_spmv_sell_kernel<T, MODE, false, true><<<grid, kSpmvThreads, 0, s>>>(
-        s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p,
-        m->hub_colstream.p, (const T *)m->sell_val.p,
-        (const T *)m->diagonal.p, xb, yb, nullptr, nullptr);
+    CFS_LAUNCH_SELL(MODE, false, true, false, m->hub_colstream.p, nullptr,
+                    nullptr);
   else if (dot)
-    sym_spmv_sell_kernel<T, 0, false, false, true>
-        <<<grid, kSpmvThreads, 0, s>>>(
-            s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
-            (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb,
-            nullptr, dot);
+    CFS_LAUNCH_SELL(0, false, false, true, m->sell_col.p, nullptr, dot);
   else
-    sym_spmv_sell_kernel<T, MODE, false, false><<<grid, kSpmvThreads, 0, s>>>(
-        s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
-        (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr,
-        nullptr);
+    CFS_LAUNCH_SELL(MODE, false, false, false, m->sell_col.p, nullptr, nullptr);
+#undef CFS_LAUNCH_SELL
   if (hubs)
     launch_hub_spmv(m, yb, xb, s);
 }
@@ -254,8 +259,10 @@ int launch_tma(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 
 template <typename T>
 int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-               cudaStream_t s, long long s0, long long s1,
+               cudaStream_t s, long long s0, long long s1, const Extras &ex,
                double *dot = nullptr) {
+  const T *xl = ex.x_lower ? (const T *)ex.x_lower : xb;
+  T *yc = (T *)ex.y_clear;
   const unsigned grid =
       (unsigned)(((s1 - s0) * 32 + reg::kThreads - 1) / reg::kThreads);
   // Row chunks of the host-vector pipeline run next to PCIe copies: a kernel
@@ -276,22 +283,61 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   const int vi = !g_options.value_index || m->ndict == 0 ? 0
                  : m->ndict == 1                        ? 2
                                                         : 1;
-#define CFS_LAUNCH_REG(HALO, DOT, VI, SMEM, YL, DOTP)                          \
-  reg::sym_spmv_reg_kernel<T, HALO, DOT, VI>                                   \
+#define CFS_LAUNCH_REG(HALO, DOT, VI, PF, SMEM, YL, DOTP)                      \
+  reg::sym_spmv_reg_kernel<T, HALO, DOT, VI, PF>                               \
       <<<grid, reg::kThreads, SMEM, s>>>(                                      \
           s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,               \
           m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,                  \
           (const T *)m->diagonal.p, xb, yb, YL, DOTP, m->vcode.p,              \
-          (const T *)m->vdict.p, m->ndict)
+          (const T *)m->vdict.p, m->ndict, 0, xl, yc)
+#define CFS_LAUNCH_BULK(HALO, DOT, YL, DOTP)                                   \
+  do {                                                                         \
+    auto kernel = reg::sym_spmv_reg_kernel<T, HALO, DOT, 0, false, true>;      \
+    static int granted_bulk = 0; /* per instantiation */                       \
+    if (granted_bulk < bulk_smem) {                                            \
+      CFS_CUDA_TRY(cudaFuncSetAttribute(                                       \
+          kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bulk_smem));    \
+      granted_bulk = bulk_smem;                                                \
+    }                                                                          \
+    kernel<<<grid, reg::kThreads, bulk_smem, s>>>(                             \
+        s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p, m->vrow_row.p,  \
+        m->ccol.p, (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, \
+        YL, DOTP, m->vcode.p, (const T *)m->vdict.p, m->ndict,                 \
+        m->max_slice_steps, xl, yc);                                           \
+  } while (0)
 #define CFS_LAUNCH_REG_VI(HALO, DOT, SMEM, YL, DOTP)                           \
   do {                                                                         \
     if (vi == 2)                                                               \
-      CFS_LAUNCH_REG(HALO, DOT, 2, SMEM, YL, DOTP);                            \
+      CFS_LAUNCH_REG(HALO, DOT, 2, false, SMEM, YL, DOTP);                     \
     else if (vi == 1)                                                          \
-      CFS_LAUNCH_REG(HALO, DOT, 1, SMEM, YL, DOTP);                            \
+      CFS_LAUNCH_REG(HALO, DOT, 1, false, SMEM, YL, DOTP);                     \
+    else if (g_options.l2_prefetch && g_options.reg_blocks == 12)              \
+      reg::sym_spmv_reg_kernel<T, HALO, DOT, 0, true, false, 12>               \
+          <<<grid, reg::kThreads, SMEM, s>>>(                                  \
+              s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,           \
+              m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,              \
+              (const T *)m->diagonal.p, xb, yb, YL, DOTP, m->vcode.p,          \
+              (const T *)m->vdict.p, m->ndict, 0, xl, yc);                     \
+    else if (g_options.l2_prefetch)                                            \
+      CFS_LAUNCH_REG(HALO, DOT, 0, true, SMEM, YL, DOTP);                      \
     else                                                                       \
-      CFS_LAUNCH_REG(HALO, DOT, 0, SMEM, YL, DOTP);                            \
+      CFS_LAUNCH_REG(HALO, DOT, 0, false, SMEM, YL, DOTP);                     \
   } while (0)
+  // variant 7: value blocks staged by the TMA engine (streamed values only)
+  const int bulk_smem =
+      128 + (reg::kThreads / 32) * m->max_slice_steps * kSliceRows * (int)sizeof(T);
+  if (g_options.spmv_variant == 7 && vi == 0 && !smem && m->max_slice_steps > 0 &&
+      bulk_smem <= 200 * 1024) {
+    if (y_lower && dot)
+      CFS_LAUNCH_BULK(true, true, y_lower, dot);
+    else if (y_lower)
+      CFS_LAUNCH_BULK(true, false, y_lower, nullptr);
+    else if (dot)
+      CFS_LAUNCH_BULK(false, true, nullptr, dot);
+    else
+      CFS_LAUNCH_BULK(false, false, nullptr, nullptr);
+    return CFS_OK;
+  }
   if (y_lower && dot)
     CFS_LAUNCH_REG_VI(true, true, 0, y_lower, dot);
   else if (y_lower)
@@ -299,17 +345,19 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   else if (dot)
     CFS_LAUNCH_REG_VI(false, true, 0, nullptr, dot);
   else if (smem) // occupancy-capped pipeline launches (measurement knob)
-    CFS_LAUNCH_REG(false, false, 0, smem, nullptr, nullptr);
+    CFS_LAUNCH_REG(false, false, 0, false, smem, nullptr, nullptr);
   else
     CFS_LAUNCH_REG_VI(false, false, 0, nullptr, nullptr);
 #undef CFS_LAUNCH_REG_VI
 #undef CFS_LAUNCH_REG
+#undef CFS_LAUNCH_BULK
   return CFS_OK;
 }
 
 template <typename T, bool HALO, bool DOT>
 int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-                    double *dot, cudaStream_t s, long long s0, long long s1) {
+                    double *dot, cudaStream_t s, long long s0, long long s1,
+                    const Extras &ex) {
   // whole tiles only: [s0, s1) starts on a tile boundary (the caller checks)
   const long long tile0 = s0 / kT6Slices;
   const long long ntiles = (s1 - s0 + kT6Slices - 1) / kT6Slices;
@@ -328,22 +376,25 @@ int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
       tile0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->t6_pack.p,
       (const T *)m->sell_val.p, (const T *)m->diagonal.p, m->t6_lo.p,
       m->t6_ncols.p, m->t6_cptr_off.p, m->t6_cptr.p, prod_entries, xb, yb,
-      y_lower, dot);
+      y_lower, dot, ex.x_lower ? (const T *)ex.x_lower : xb, (T *)ex.y_clear);
   return CFS_OK;
 }
 
 template <typename T>
 int launch_tile6(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
-                 double *dot, cudaStream_t s, long long s0, long long s1) {
+                 double *dot, cudaStream_t s, long long s0, long long s1,
+                 const Extras &ex) {
   if (y_lower && dot)
-    return launch_tile6_as<T, true, true>(m, xb, yb, y_lower, dot, s, s0, s1);
+    return launch_tile6_as<T, true, true>(m, xb, yb, y_lower, dot, s, s0, s1,
+                                          ex);
   if (y_lower)
     return launch_tile6_as<T, true, false>(m, xb, yb, y_lower, nullptr, s, s0,
-                                           s1);
+                                           s1, ex);
   if (dot)
-    return launch_tile6_as<T, false, true>(m, xb, yb, nullptr, dot, s, s0, s1);
+    return launch_tile6_as<T, false, true>(m, xb, yb, nullptr, dot, s, s0, s1,
+                                           ex);
   return launch_tile6_as<T, false, false>(m, xb, yb, nullptr, nullptr, s, s0,
-                                          s1);
+                                          s1, ex);
 }
 
 template <typename T>
@@ -357,12 +408,17 @@ int launch_win(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
 template <typename T>
 int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                      void *y_lower_base, cudaStream_t s, long long s0,
-                     long long s1, double *dot) {
+                     long long s1, double *dot, Extras ex) {
+  // the row owners index y_clear by global row id like y
+  if (ex.y_clear)
+    ex.y_clear = (T *)ex.y_clear - m->halo_begin;
   const T *xb = (const T *)x_ext - m->halo_begin;
   T *yb = (T *)y_ext - m->halo_begin;
   T *yl = (T *)y_lower_base;
   const int mode = g_options.diag_mode;
   int variant = g_options.spmv_variant;
+  if (variant == 7)
+    variant = 5; // the same kernel with TMA-staged value blocks (launch_reg)
   const bool partial = s0 != 0 || s1 != m->nslices;
   // bounded column windows (banded / FEM orderings): products transposed
   // through shared memory, one coalesced RED per column and tile
@@ -370,19 +426,19 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   if ((variant == 5 || variant == 6) && m->nt6 > 0 && g_options.tile6 &&
       mode == 0 && s0 % kT6Slices == 0 &&
       (s1 % kT6Slices == 0 || s1 == m->nslices))
-    return launch_tile6<T>(m, xb, yb, yl, dot, s, s0, s1);
-  if ((yl || partial || dot) && variant != 1)
+    return launch_tile6<T>(m, xb, yb, yl, dot, s, s0, s1, ex);
+  if ((yl || partial || dot || ex.y_clear) && variant != 1)
     variant = 5; // halo fusion / slice ranges / x'Ax exist in the register kernels
   // bulk copies of the x / y windows need 16-byte aligned vectors
   // the compressed-index kernel pays off when slices are regular; ragged
   // matrices run the generic warp-per-slice kernel (more registers, no spills)
   if (variant == 5 && m->ccol.p && mode == 0 &&
       m->nregular * 8 >= m->nslices)
-    return launch_reg<T>(m, xb, yb, yl, s, s0, s1, dot);
-  if (variant == 5 || yl || partial || dot)
+    return launch_reg<T>(m, xb, yb, yl, s, s0, s1, ex, dot);
+  if (variant == 5 || yl || partial || dot || ex.y_clear)
     variant = 1;
   if (dot) {
-    launch_sell<T, 0>(m, xb, yb, yl, s, s0, s1, dot);
+    launch_sell<T, 0>(m, xb, yb, yl, s, s0, s1, ex, dot);
     return CFS_OK;
   }
   if (variant >= 3 &&
@@ -408,16 +464,16 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   }
   switch (mode) {
   case 1:
-    launch_sell<T, 1>(m, xb, yb, yl, s, s0, s1);
+    launch_sell<T, 1>(m, xb, yb, yl, s, s0, s1, ex);
     break;
   case 2:
-    launch_sell<T, 2>(m, xb, yb, yl, s, s0, s1);
+    launch_sell<T, 2>(m, xb, yb, yl, s, s0, s1, ex);
     break;
   case 3:
-    launch_sell<T, 3>(m, xb, yb, yl, s, s0, s1);
+    launch_sell<T, 3>(m, xb, yb, yl, s, s0, s1, ex);
     break;
   default:
-    launch_sell<T, 0>(m, xb, yb, yl, s, s0, s1);
+    launch_sell<T, 0>(m, xb, yb, yl, s, s0, s1, ex);
     break;
   }
   return CFS_OK;
@@ -428,7 +484,11 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
 int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1,
                     void *y_lower_base, bool y_is_zero, long long slice0,
-                    long long slice1, double *xdoty) {
+                    long long slice1, double *xdoty, const void *x_lower_base,
+                    void *y_clear) {
+  Extras ex;
+  ex.x_lower = x_lower_base;
+  ex.y_clear = y_clear;
   if (slice1 < 0)
     slice1 = m->nslices;
   const size_t vs = m->vsize();
@@ -441,9 +501,9 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
     CFS_CUDA_TRY(cudaEventRecord(ev0, s));
   CFS_TRY(m->is_double
               ? launch_sym_typed<double>(m, y_ext, x_ext, y_lower_base, s,
-                                         slice0, slice1, xdoty)
+                                         slice0, slice1, xdoty, ex)
               : launch_sym_typed<float>(m, y_ext, x_ext, y_lower_base, s,
-                                        slice0, slice1, xdoty));
+                                        slice0, slice1, xdoty, ex));
   CFS_CUDA_TRY(cudaGetLastError());
   if (ev1)
     CFS_CUDA_TRY(cudaEventRecord(ev1, s));

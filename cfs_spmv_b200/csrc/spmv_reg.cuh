@@ -76,8 +76,40 @@ __device__ __forceinline__ unsigned ld_stream(const unsigned char *p) {
   return v;
 }
 
-template <typename T, bool HALO, bool DOT = false, int VI = 0>
-__global__ void __launch_bounds__(kThreads, 16)
+// S += r on the lanes where `upper` holds, E += r on the others -- as two
+// predicated adds (the compiler's if-conversion makes two adds and four selects)
+__device__ __forceinline__ void split_add(double &S, double &E, bool upper,
+                                          double r) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t"
+      "@p add.f64 %0, %0, %3;\n\t@!p add.f64 %1, %1, %3;\n\t}"
+      : "+d"(S), "+d"(E)
+      : "r"((int)upper), "d"(r));
+}
+__device__ __forceinline__ void split_add(float &S, float &E, bool upper,
+                                          float r) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t"
+      "@p add.f32 %0, %0, %3;\n\t@!p add.f32 %1, %1, %3;\n\t}"
+      : "+f"(S), "+f"(E)
+      : "r"((int)upper), "f"(r));
+}
+
+// PF: the warp asks L2 for its slice's whole value block (w x 256 B for f64)
+// before it touches the first entry -- one prefetch.global.L2 per 128-byte line,
+// dealt out over the lanes. The kernel is bound by bytes in flight, not by
+// DRAM: at 32 registers a warp can hold one chain (<= 768 B) of value loads,
+// and the prefetches put the other ~2.5 KB of the slice on their way without a
+// single register. The loads behind them then meet L2 latency instead of DRAM
+// latency.
+//
+// BULK (variant 7): instead, lane 0 hands the whole value block of the slice to
+// the TMA engine -- ONE cp.async.bulk (SASS UBLKCP) into this warp's piece of
+// shared memory, completion on a per-warp mbarrier -- and the warp goes on
+// loading its row tags, x[row], the diagonal and the column bases while the
+// block is in flight. bulk_steps = the widest slice of the matrix (the stride
+// of a warp's piece). Copies of different warps overlap (tools/tma_bench.cu).
+template <typename T, bool HALO, bool DOT = false, int VI = 0, bool PF = false,
+          bool BULK = false, int MINB = 16>
+__global__ void __launch_bounds__(kThreads, MINB)
     sym_spmv_reg_kernel(long long slice_begin, long long slice_end,
                         int row_begin,
                         const int *__restrict__ slice_ptr,
@@ -89,7 +121,10 @@ __global__ void __launch_bounds__(kThreads, 16)
                         const T *__restrict__ x, T *__restrict__ y,
                         T *__restrict__ y_lower, double *__restrict__ dot,
                         const unsigned char *__restrict__ vcode,
-                        const T *__restrict__ vdict, int ndict) {
+                        const T *__restrict__ vdict, int ndict,
+                        int bulk_steps, const T *__restrict__ x_lower,
+                        T *__restrict__ y_clear) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ T sdict[VI == 1 ? kMaxDict : 1];
   T one_value = T(0);
   if (VI == 1) {
@@ -104,8 +139,38 @@ __global__ void __launch_bounds__(kThreads, 16)
       slice_begin + ((blockIdx.x * (long long)kThreads + threadIdx.x) >> 5);
   if (s >= slice_end)
     return;
-  const int tag = vrow_row[s * kSliceRows + lane];
   const int p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
+  const T *sval = nullptr; // BULK: this warp's value block in shared memory
+  uint64_t *bar = nullptr;
+  if (BULK) {
+    const int warp = threadIdx.x >> 5;
+    bar = reinterpret_cast<uint64_t *>(dyn_smem) + warp;
+    T *dst = reinterpret_cast<T *>(dyn_smem + 128) +
+             (size_t)warp * bulk_steps * kSliceRows;
+    sval = dst + lane;
+    if (lane == 0) {
+      tma::mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (p1 > p0) {
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;"
+                     : "=l"(policy));
+        const uint32_t bytes =
+            (uint32_t)(p1 - p0) * kSliceRows * (uint32_t)sizeof(T);
+        tma::mbar_expect_tx(bar, bytes);
+        tma::load_1d(dst, sell_val + (size_t)p0 * kSliceRows, bytes, bar,
+                     policy);
+      }
+    }
+    __syncwarp();
+  }
+  if (PF && VI == 0 && !BULK) {
+    const char *blk = reinterpret_cast<const char *>(sell_val + (size_t)p0 * kSliceRows);
+    const int bytes = (p1 - p0) * kSliceRows * (int)sizeof(T);
+    for (int off = lane * 128; off < bytes; off += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + off));
+  }
+  const int tag = vrow_row[s * kSliceRows + lane];
   const int cptr = slice_cptr[s];
   const bool active = tag >= 0;
   const int row = tag & kVrowRowMask;
@@ -126,6 +191,8 @@ __global__ void __launch_bounds__(kThreads, 16)
       return one_value;
     if (VI == 1)
       return sdict[ld_stream(kp + (size_t)step * kSliceRows)];
+    if (BULK)
+      return sval[step * kSliceRows];
     return ld_stream(vp + (size_t)step * kSliceRows);
   };
 
@@ -135,46 +202,74 @@ __global__ void __launch_bounds__(kThreads, 16)
     const int nb = __shfl_down_sync(0xffffffffu, base, 1);
     const unsigned cont =
         __ballot_sync(0xffffffffu, lane + 1 < w && nb == base + 1);
+    if (BULK && w > 0)
+      tma::mbar_wait(bar, 0);
+    // The kernel is bound by instruction issue once the value stream is
+    // compressed or prefetched (ncu, round 1: issue slots 72 %), so the chain
+    // lengths are separate straight-line paths -- no predicated slots for the
+    // entries a shorter chain does not have -- and the split of a rotated
+    // product into S (lanes >= j) and E (the j lanes that wrapped) is two
+    // predicated adds instead of adds + selects.
     for (int k = 0; k < w;) {
-      int L = 1;
-      while (L < kMaxChain && ((cont >> (k + L - 1)) & 1u))
-        ++L;
       const int cbase = __shfl_sync(0xffffffffu, base, k);
-      T a[kMaxChain], xc[kMaxChain];
-#pragma unroll
-      for (int j = 0; j < kMaxChain; ++j) {
-        a[j] = T(0);
-        xc[j] = T(0);
-        if (j < L) {
-          a[j] = value_at(k + j);
-          xc[j] = x[cbase + lane + j];
-        }
+      const unsigned bits = cont >> k;
+      const T *xp = x + cbase + lane;
+      const bool halo = HALO && cbase < row_begin; // warp-uniform
+      // x of the chain's window; a window that reaches below row_begin reads
+      // those entries from the GPU below
+      auto xv = [&](int j) -> T {
+        if (HALO && halo)
+          return tma::x_at<true>(x, x_lower, row_begin, cbase + lane + j);
+        return xp[j];
+      };
+      T S, E = T(0);
+      int L;
+      if ((bits & 3u) == 3u) {
+        L = 3;
+        const T a0 = value_at(0), a1 = value_at(1), a2 = value_at(2);
+        const T x0 = xv(0), x1 = xv(1), x2 = xv(2);
+        acc += a0 * x0;
+        acc += a1 * x1;
+        acc += a2 * x2;
+        S = a0 * xr;
+        const T r1 = __shfl_sync(0xffffffffu, a1 * xr, (lane - 1) & 31);
+        const T r2 = __shfl_sync(0xffffffffu, a2 * xr, (lane - 2) & 31);
+        split_add(S, E, lane >= 1, r1);
+        split_add(S, E, lane >= 2, r2);
+      } else if (bits & 1u) {
+        L = 2;
+        const T a0 = value_at(0), a1 = value_at(1);
+        const T x0 = xv(0), x1 = xv(1);
+        acc += a0 * x0;
+        acc += a1 * x1;
+        S = a0 * xr;
+        const T r1 = __shfl_sync(0xffffffffu, a1 * xr, (lane - 1) & 31);
+        split_add(S, E, lane >= 1, r1);
+      } else {
+        L = 1;
+        const T a0 = value_at(0);
+        acc += a0 * xv(0);
+        S = a0 * xr;
       }
-      T S = T(0), E = T(0);
-#pragma unroll
-      for (int j = 0; j < kMaxChain; ++j) {
-        if (j < L) { // warp-uniform
-          acc += a[j] * xc[j];
-          const T p = a[j] * xr;
-          const T r = j == 0 ? p : __shfl_sync(0xffffffffu, p, (lane - j) & 31);
-          if (lane >= j)
-            S += r;
-          else
-            E += r;
-        }
-      }
-      if (HALO && cbase < row_begin) { // warp-uniform: chain reaches the halo
+      if (halo) { // chain reaches the rows of the GPU below
         tma::y_add<true>(y, y_lower, row_begin, cbase + lane, S);
         if (lane < L - 1)
           tma::y_add<true>(y, y_lower, row_begin, cbase + kSliceRows + lane, E);
       } else {
-        tma::red_add(y + cbase + lane, S);
+        T *yp = y + cbase + lane;
+        tma::red_add(yp, S);
         if (lane < L - 1)
-          tma::red_add(y + cbase + kSliceRows + lane, E);
+          tma::red_add(yp + kSliceRows, E);
       }
       k += L;
+      vp += L * kSliceRows; // running pointers: value_at(j) is one add away
+      kp += L * kSliceRows;
+      if (BULK)
+        sval += L * kSliceRows;
     }
   } else {
+    if (BULK && w > 0)
+      tma::mbar_wait(bar, 0);
     for (; w >= kUnroll; w -= kUnroll) {
       int c[kUnroll];
       T a[kUnroll];
@@ -186,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 16)
       T xc[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
-        xc[u] = c[u] >= 0 ? x[c[u]] : T(0);
+        xc[u] = c[u] >= 0 ? tma::x_at<HALO>(x, x_lower, row_begin, c[u]) : T(0);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         if (c[u] >= 0) {
@@ -197,21 +292,30 @@ __global__ void __launch_bounds__(kThreads, 16)
       cp += kUnroll * kSliceRows;
       vp += kUnroll * kSliceRows;
       kp += kUnroll * kSliceRows;
+      if (BULK)
+        sval += kUnroll * kSliceRows;
     }
     for (; w > 0; --w) {
       const int c = ld_stream(cp);
       const T a = value_at(0);
       if (c >= 0) {
-        acc += a * x[c];
+        acc += a * tma::x_at<HALO>(x, x_lower, row_begin, c);
         tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
       }
       cp += kSliceRows;
       vp += kSliceRows;
       kp += kSliceRows;
+      if (BULK)
+        sval += kSliceRows;
     }
   }
-  if (active)
+  if (active) {
     tma::red_add(y + row, acc);
+    // ping-pong result vectors: the row's owner clears the OTHER vector for the
+    // next SpMV, which then needs no separate y initialisation
+    if (y_clear && !(tag & kVrowCont))
+      y_clear[row] = T(0);
+  }
   if (DOT) {
     double c = (double)xr * (2.0 * (double)acc - (double)dterm);
 #pragma unroll

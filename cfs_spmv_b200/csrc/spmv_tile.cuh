@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(kThreads, 2)
                          const unsigned short *__restrict__ cptr,
                          int prod_entries,
                          const T *__restrict__ x, T *__restrict__ y,
-                         T *__restrict__ y_lower, double *__restrict__ dot) {
+                         T *__restrict__ y_lower, double *__restrict__ dot,
+                         const T *__restrict__ x_lower,
+                         T *__restrict__ y_clear) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *prod = reinterpret_cast<T *>(smem_raw);
   // the slot offsets of the tile's columns, staged before phase 1 so that
@@ -111,7 +113,10 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        xc[u] = p[u] != 0xffffffffu ? x[lo + (int)(p[u] & 0xffffu)] : T(0);
+        xc[u] = p[u] != 0xffffffffu
+                    ? tma::x_at<HALO>(x, x_lower, row_begin,
+                                      lo + (int)(p[u] & 0xffffu))
+                    : T(0);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (p[u] != 0xffffffffu) {
@@ -126,14 +131,18 @@ __global__ void __launch_bounds__(kThreads, 2)
       const unsigned p = ld_stream(pp);
       const T a = ld_stream(vp);
       if (p != 0xffffffffu) {
-        acc += a * x[lo + (int)(p & 0xffffu)];
+        acc += a * tma::x_at<HALO>(x, x_lower, row_begin,
+                                   lo + (int)(p & 0xffffu));
         prod[p >> 16] = a * xr;
       }
       pp += kSliceRows;
       vp += kSliceRows;
     }
-    if (active)
+    if (active) {
       tma::red_add(y + row, acc);
+      if (y_clear && !(tag & kVrowCont)) // see spmv_reg.cuh
+        y_clear[row] = T(0);
+    }
     if (DOT) { // x'(A x), see spmv_reg.cuh
       double c = (double)xr * (2.0 * (double)acc - (double)dterm);
 #pragma unroll

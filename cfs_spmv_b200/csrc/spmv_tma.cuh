@@ -89,6 +89,18 @@ __device__ __forceinline__ void y_add(T *y, T *y_lower, int row_begin, int col,
     red_add(y + col, v);
 }
 
+// x[col]. With HALO the columns below row_begin are rows of the GPU below: they
+// are read straight from ITS x over NVLink (x_lower is that vector's virtual
+// base pointer; a caller that has pulled the halo into its own vector passes
+// its own base) -- no copy step before the kernel.
+template <bool HALO, typename T>
+__device__ __forceinline__ T x_at(const T *x, const T *x_lower, int row_begin,
+                                  int col) {
+  if (HALO && col < row_begin)
+    return x_lower[col];
+  return x[col];
+}
+
 constexpr int kTileRows = kTileSlices * kSliceRows;
 
 // The part of a TileRec an issuing lane keeps in registers.

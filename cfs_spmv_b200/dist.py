@@ -109,16 +109,25 @@ class HaloExchanger:
 class P2PHalo:
     """Halo handling over peer memory (NVLink) instead of NCCL messages.
 
-    x_ext / y_ext of every rank live in symmetric memory
-    (torch.distributed._symmetric_memory: plumbing that maps each rank's buffer
-    into the others and provides a device-side barrier). Per step:
-      clear y -> barrier -> pull the x halo from the GPU below (peer load) ->
-      SpMV kernel that reduces its halo contributions straight into the y of
-      the GPU below (cfs_cuda_spmv_halo_async) -> barrier.
+    x_ext and TWO y_ext vectors of every rank live in symmetric memory
+    (torch.distributed._symmetric_memory: plumbing that maps each rank's
+    buffers into the others and provides a device-side barrier). One step =
+
+      ONE kernel (cfs_cuda_spmv_shard_async): reads its x halo straight from
+      the x of the GPU below, reduces its halo contributions straight into the
+      y of the GPU below (RED.sys over NVLink), and its row owners clear the
+      OTHER y vector, which the next step reduces into;
+      ONE barrier: all reductions have landed, every "other" vector is clear.
+
+    Round 1 needed a y memset, a barrier, an x-halo copy, the kernel and a
+    second barrier per step (45-60 us around a 150 us kernel). A caller that
+    rewrites x between two steps synchronises once more before the kernel
+    (`x_changed=True`): the GPU above reads this GPU's x.
     Needs every halo to lie inside the row block of ONE lower neighbour (true
     for stencil and banded matrices)."""
 
     def __init__(self, ranges, rank, dtype, device):
+        import os
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -130,31 +139,55 @@ class P2PHalo:
                                    "neighbour" % g)
         max_len = max(e - h for h, b, e in ranges)
         self.x_sym = symm_mem.empty(max_len, dtype=dtype, device=device)
-        self.y_sym = symm_mem.empty(max_len, dtype=dtype, device=device)
+        self.y_sym = symm_mem.empty(2 * max_len, dtype=dtype, device=device)
         self.hx = symm_mem.rendezvous(self.x_sym, dist.group.WORLD)
         self.hy = symm_mem.rendezvous(self.y_sym, dist.group.WORLD)
         n = self.e - self.h
+        item = self.x_sym.element_size()
         self.x_ext = self.x_sym[:n]
-        self.y_ext = self.y_sym[:n]
-        self.y_lower_base = None
+        self.y_bufs = [self.y_sym[:n], self.y_sym[max_len:max_len + n]]
+        self.y_lower_bases = [None, None]
+        self.x_lower_base = None
         self.x_peer = None
         self.nhalo = self.b - self.h
         if rank > 0 and self.nhalo > 0:
             ph = ranges[rank - 1][0]
-            item = self.x_sym.element_size()
-            self.y_lower_base = self.hy.buffer_ptrs[rank - 1] - ph * item
+            y_peer = self.hy.buffer_ptrs[rank - 1]
+            self.y_lower_bases = [y_peer - ph * item,
+                                  y_peer + (max_len - ph) * item]
+            self.x_lower_base = self.hx.buffer_ptrs[rank - 1] - ph * item
             peer_x = self.hx.get_buffer(rank - 1, (max_len,), dtype)
             self.x_peer = peer_x[self.h - ph:self.b - ph]
-        self.bytes_per_step = 2 * self.nhalo * self.x_sym.element_size()
-        import os
+        self.bytes_per_step = 2 * self.nhalo * item
         self.sync = os.environ.get("CFS_GPU_HALO_SYNC", "barrier")
+        self.t = 0
+        self.reset()
 
-    # Synchronisation of a step. "barrier": two device barriers over all ranks.
-    # "neighbour" (CFS_GPU_HALO_SYNC=neighbour): the dependencies are only
-    # between adjacent row blocks, so a rank signals / waits for its two
-    # neighbours through the signal pads of the symmetric memory instead:
-    #   before the kernel  r -> r+1 : "my y is clear and my x is final"
-    #   after the kernel   r -> r-1 : "my reductions into your y have landed"
+    # the older, bulk-synchronous pieces (DistributedCG uses them: its SpMV
+    # also returns p'Ap): result in y_bufs[0], x halo pulled by a peer copy
+    @property
+    def y_ext(self):
+        return self.y_bufs[0]
+
+    @property
+    def y_lower_base(self):
+        return self.y_lower_bases[0]
+
+    def reset(self):
+        """both result vectors clear on every rank"""
+        self.y_sym.zero_()
+        self.t = 0
+        self.hy.barrier()
+
+    @property
+    def y_current(self):
+        """the vector the last step() left y in"""
+        return self.y_bufs[(self.t - 1) % 2] if self.t else self.y_bufs[0]
+
+    # Synchronisation of the bulk-synchronous pieces. "barrier": device
+    # barriers over all ranks. "neighbour" (CFS_GPU_HALO_SYNC=neighbour): a
+    # rank signals / waits for its two neighbours through the signal pads of
+    # the symmetric memory instead.
     _TIMEOUT_MS = 20000
 
     def sync_before(self):
@@ -175,28 +208,36 @@ class P2PHalo:
         if self.rank + 1 < self.world:
             self.hy.wait_signal(self.rank + 1, 1, self._TIMEOUT_MS)
 
-    def step(self, matrix, stream):
-        self.y_ext.zero_()
-        self.sync_before()             # y below is clear, x below is final
-        if self.x_peer is not None:
-            self.x_ext[:self.nhalo].copy_(self.x_peer)
-        matrix.spmv_halo_async(self.y_ext, self.x_ext, self.y_lower_base, True,
-                               stream)
-        self.sync_after()              # all halo reductions have landed
+    def step(self, matrix, stream, x_changed=False):
+        if x_changed:
+            self.hy.barrier()          # x below is final
+        k = self.t % 2
+        matrix.spmv_shard_async(self.y_bufs[k], self.x_ext,
+                                self.y_lower_bases[k], self.x_lower_base,
+                                self.y_bufs[1 - k], True, stream)
+        self.hy.barrier()              # reductions landed, other vector clear
+        self.t += 1
+        return self.y_bufs[k]
 
 
 class ShardedSpMV:
-    """One rank's share of y = A*x for a generated matrix (bench / tests)."""
+    """One rank's share of y = A*x for a generated matrix (bench / tests).
+    spec: a capi.GenSpec; or arrays=(n, rowptr, colind, values) device tensors
+    of the whole matrix (world 1: R-MAT, which needs a global sort to build)."""
 
-    def __init__(self, spec, rank, world, is_double=True, xseed=1):
+    def __init__(self, spec, rank, world, is_double=True, xseed=1, arrays=None):
+        import os
         import torch
         import torch.distributed as dist
         from . import capi
         self.rank, self.world = rank, world
-        n = spec.nrows
-        bounds = row_blocks(n, world)
-        b, e = bounds[rank], bounds[rank + 1]
-        rp, ci, v = capi.gen_device_csr(spec, b, e, is_double)
+        if arrays is not None:
+            assert world == 1, "array input: one GPU"
+            n, rp, ci, v = arrays
+            b, e = 0, n
+        else:
+            n = spec.nrows
+            b, e, rp, ci, v = self._balanced_shard(spec, rank, world, is_double)
         if world == 1:
             self.matrix = capi.Matrix(n, n, rp, ci, v, is_double, True)
         else:
@@ -215,9 +256,9 @@ class ShardedSpMV:
             ranges = [tuple(int(v) for v in t.tolist()) for t in allr]
         else:
             ranges = [(h, b, e)]
+        self.ranges = ranges
         x_gen = capi.gen_device_x(xseed, h, e, is_double)
         self.p2p = None
-        import os
         mode = os.environ.get("CFS_GPU_HALO", "p2p" if world > 1 else "none")
         if world > 1 and mode == "p2p":
             try:
@@ -231,43 +272,154 @@ class ShardedSpMV:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 0:
                 self.p2p = None
+        # single GPU: the same ping-pong of two result vectors drops the y
+        # initialisation from a loop of SpMVs (CFS_GPU_PINGPONG=0: memset + kernel)
+        self.pingpong = (world == 1 and self.info["symmetric"] == 1 and
+                         os.environ.get("CFS_GPU_PINGPONG", "1") != "0")
+        self.t = 0
         if self.p2p is not None:
-            self.x_ext, self.y_ext = self.p2p.x_ext, self.p2p.y_ext
+            self.x_ext = self.p2p.x_ext
             self.x_ext.copy_(x_gen)
-            self.y_ext.zero_()
+            self.y_bufs = self.p2p.y_bufs
+            dist.barrier()
         else:
             self.x_ext = x_gen
             # the halo part of x is (re)filled by exchange_x every step
-            self.y_ext = torch.zeros_like(self.x_ext)
+            self.y_bufs = [torch.zeros_like(self.x_ext),
+                           torch.zeros_like(self.x_ext)]
+        self.y_ext = self.y_bufs[0]
         self.halo = HaloExchanger(ranges, rank, self.x_ext)
         nh = len(self.halo.recv_x) + len(self.halo.send_x)
+        hubs = 1 if self.info["hub_columns"] else 0
         if world == 1:
-            self.exchange_desc = "none (single GPU)"
+            self.exchange_desc = "none (single GPU)" + (
+                "; y initialisation fused into the previous SpMV (two result "
+                "vectors used alternately)" if self.pingpong else "")
+            self.kernels_per_step = 1 + hubs
         elif self.p2p is not None:
             self.exchange_desc = (
-                "fused over NVLink peer memory: x halo pulled from the GPU "
-                "below, y halo contributions reduced by the SpMV kernel straight "
-                "into its y (RED.sys); %s per step; %d bytes on "
-                "rank %d" % ("neighbour signals (put / wait) before and after "
-                             "the kernel" if self.p2p.sync == "neighbour"
-                             else "2 device barriers",
-                             self.p2p.bytes_per_step, rank))
+                "fused over NVLink peer memory: ONE kernel per step reads its x "
+                "halo from the GPU below, reduces its y halo contributions "
+                "straight into that GPU's y (RED.sys) and clears the other of "
+                "two result vectors; ONE device barrier per step; %d bytes on "
+                "rank %d" % (self.p2p.bytes_per_step, rank))
+            self.kernels_per_step = 2  # SpMV + the symmetric-memory barrier
         else:
             self.exchange_desc = (
                 "NCCL P2P per step: x halo down-up, y halo strip add; "
                 "%d neighbour segments, %d bytes on rank %d" % (
                     nh, self.halo.bytes_per_step, rank))
+            self.kernels_per_step = 1 + hubs + len(self.halo.send_x)
         self._host = None
 
-    def step(self):
+    @staticmethod
+    def _balanced_shard(spec, rank, world, is_double):
+        """this rank's rows: contiguous, 16-row aligned blocks holding about the
+        same number of stored entries (partition_by_nnz semantics,
+        csr_matrix.tpp:438-541, lifted to GPUs). Every rank counts the entries
+        of an equal-rows block, the counts per 1024-row chunk are exchanged and
+        the boundaries moved to the chunk where the prefix sum crosses
+        g/world; a rank whose block moved generates its rows again."""
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        n = spec.nrows
+        eq = row_blocks(n, world)
+        b, e = eq[rank], eq[rank + 1]
+        rp, ci, v = capi.gen_device_csr(spec, b, e, is_double)
+        if world == 1:
+            return b, e, rp, ci, v
+        chunk = 1024
+        nchunks = (n + chunk - 1) // chunk
+        mine = torch.zeros(nchunks, dtype=torch.int64, device="cuda")
+        # equal-rows blocks are 16-row aligned, chunks start at multiples of
+        # 1024: a chunk can straddle two blocks, both add their part
+        rows = torch.arange(b, e, device="cuda")
+        cnt = (rp[1:] - rp[:-1]).to(torch.int64)
+        mine.index_add_(0, rows // chunk, cnt)
+        dist.all_reduce(mine)
+        prefix = torch.zeros(nchunks + 1, dtype=torch.int64)
+        prefix[1:] = torch.cumsum(mine.cpu(), 0)
+        # rows of chunk boundaries -> nnz_balanced_blocks on the coarse prefix
+        cb = nnz_balanced_blocks(prefix.numpy(), world, align=1)
+        bounds = [min(n, c * chunk) for c in cb]
+        bounds[-1] = n
+        if any(bounds[g + 1] <= bounds[g] for g in range(world)):
+            bounds = eq  # too few rows for chunk-wise balancing
+        nb, ne = bounds[rank], bounds[rank + 1]
+        if (nb, ne) != (b, e):
+            del rp, ci, v, rows, cnt
+            torch.cuda.empty_cache()
+            rp, ci, v = capi.gen_device_csr(spec, nb, ne, is_double)
+        return nb, ne, rp, ci, v
+
+    def kernel_desc(self):
+        inf = self.info
+        t = "double" if inf["is_double"] else "float"
+        if inf.get("transposed_tiles"):
+            return ("sym_spmv_tile_kernel<%s> (variant 6: transposed term "
+                    "transposed through shared memory, one coalesced RED per "
+                    "column and tile)" % t)
+        if inf["regular_slices"] * 8 >= inf["nslices"]:
+            return ("sym_spmv_reg_kernel<%s> (variant 5: compressed index "
+                    "stream, shuffle-merged REDs, %s)" % (
+                        t, "values dictionary-coded: %d distinct value(s), "
+                           "lossless" % inf["value_dictionary"]
+                        if inf.get("value_dictionary") else
+                        "8-byte values streamed behind L2 prefetches"))
+        return ("sym_spmv_sell_kernel<%s> (variant 1: one warp per slice of 32 "
+                "length-sorted virtual rows%s)" % (
+                    t, " + hub_spmv_kernel: %d hub columns run column-wise" %
+                    inf["hub_columns"] if inf["hub_columns"] else ""))
+
+    def step(self, x_changed=False):
         import torch
         s = torch.cuda.current_stream().cuda_stream
         if self.p2p is not None:
-            self.p2p.step(self.matrix, s)
+            self.y_ext = self.p2p.step(self.matrix, s, x_changed)
+            return
+        if self.pingpong:
+            k = self.t % 2
+            self.matrix.spmv_shard_async(self.y_bufs[k], self.x_ext, None, None,
+                                         self.y_bufs[1 - k], True, s)
+            self.y_ext = self.y_bufs[k]
+            self.t += 1
             return
         self.halo.exchange_x(self.x_ext)
         self.matrix.spmv_async(self.y_ext, self.x_ext, s)
         self.halo.reduce_y(self.y_ext)
+
+    def time_kernel(self, iters):
+        """average device time (ms) of the SpMV kernel alone: `iters` launches
+        back to back between two CUDA events, the two result vectors used
+        alternately (each launch clears the vector the next one reduces into),
+        no halo exchange and no barrier -- a shard reduces its halo
+        contributions into the halo part of its own vector"""
+        import torch
+        s = torch.cuda.current_stream()
+        bufs = self.y_bufs
+        if self.p2p is not None:  # private vectors: nothing of a neighbour's
+            bufs = [torch.zeros_like(self.x_ext), torch.zeros_like(self.x_ext)]
+        if self.info["symmetric"] != 1:
+            raise RuntimeError("time_kernel: symmetric matrices only")
+        for b in bufs:
+            b.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        for k in range(2):  # warm
+            self.matrix.spmv_shard_async(bufs[k], self.x_ext, None, None,
+                                         bufs[1 - k], True, s.cuda_stream)
+        e0.record(s)
+        for k in range(iters):
+            self.matrix.spmv_shard_async(bufs[k % 2], self.x_ext, None, None,
+                                         bufs[1 - k % 2], True, s.cuda_stream)
+        e1.record(s)
+        e1.synchronize()
+        if self.p2p is None:  # leave the step's invariant behind: both clear
+            for b in self.y_bufs:
+                b.zero_()
+            self.t = 0
+        return e0.elapsed_time(e1) / iters
 
     def y_owned(self):
         return self.y_ext[self.b - self.h:]
@@ -287,6 +439,7 @@ class ShardedSpMV:
         import torch
         n_own = self.e - self.b
         if self.world == 1:
+            y_dev = self.y_owned().clone()
             x_host = self.x_ext.cpu().pin_memory()
             y_host = torch.empty_like(x_host).pin_memory()
             self.matrix.spmv(y_host, x_host)  # allocates the staging buffers
@@ -295,9 +448,10 @@ class ShardedSpMV:
             for _ in range(steps):
                 self.matrix.spmv(y_host, x_host)  # synchronous C ABI call
             ms = (time.perf_counter() - t0) * 1e3
-            err = (y_host - self.y_owned().cpu()).abs().max().item()
-            scale = self.y_owned().abs().max().item()
-            assert err <= 1e-9 * max(scale, 1.0), "e2e result differs"
+            err = (y_host - y_dev.cpu()).abs().max().item()
+            scale = y_dev.abs().max().item()
+            tol = 1e-9 if y_dev.dtype == torch.float64 else 1e-3
+            assert err <= tol * max(scale, 1.0), "e2e result differs"
             return ms, x_host.numel() * x_host.element_size(), \
                 y_host.numel() * y_host.element_size()
         x_host = self.x_ext.cpu().pin_memory()       # owned rows + halo
@@ -307,8 +461,10 @@ class ShardedSpMV:
         def one():
             self.x_ext.copy_(x_host, non_blocking=True)
             if self.p2p is not None:
-                self.p2p.step(self.matrix, s.cuda_stream)
+                # every rank's x has just been rewritten: synchronise first
+                self.y_ext = self.p2p.step(self.matrix, s.cuda_stream, True)
             else:
+                self.halo.exchange_x(self.x_ext)
                 self.matrix.spmv_async(self.y_ext, self.x_ext, s.cuda_stream)
                 self.halo.reduce_y(self.y_ext)
             y_host.copy_(self.y_owned(), non_blocking=True)

@@ -240,6 +240,25 @@ int cfs_cuda_spmv_async(cfs_mat_t m, void *y_dev, const void *x_dev,
 int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                              void *y_lower_base, int y_is_zero, void *stream);
 
+/* The same with the two things that take the step's skeleton off the critical
+ * path (the kernel is 150 us; a y initialisation, an x-halo copy and a second
+ * barrier around it cost 45-60 us more in round 1):
+ *   x_lower_base: the x vector of the GPU below as a peer-mapped virtual base
+ *     (like y_lower_base): halo entries of x are read from there by the kernel,
+ *     no copy into the local halo beforehand; NULL: the local halo part of x_dev
+ *     holds them;
+ *   y_clear: a second vector like y_dev whose OWNED rows the kernel clears (one
+ *     store per row by the lane that owns the row): with two result vectors
+ *     used alternately, SpMV k clears the one SpMV k+1 reduces into, and no
+ *     separate initialisation is left -- one synchronisation of the GPUs per
+ *     SpMV (after it: reductions landed, other vector clear, x final) is then
+ *     enough. NULL: no clearing.
+ * Also usable on an unsharded matrix (y_lower_base = x_lower_base = NULL) to
+ * drop the y initialisation from a loop of SpMVs. */
+int cfs_cuda_spmv_shard_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                              void *y_lower_base, const void *x_lower_base,
+                              void *y_clear, int y_is_zero, void *stream);
+
 /* ---- conjugate gradients on the device: solves A x = b
  * for a tuned symmetric positive definite matrix with the SpMV above as its
  * only matrix operation. The reference has no solver; this is the loop its
@@ -286,10 +305,11 @@ int cfs_cuda_cg_update_p(int64_t n, int is_double, const double *scal,
                          const void *r, void *p, void *stream);
 
 /* Measurement aid for bench.py (bench_spmv_mmf.cpp:162-167 times the same
- * loop with omp_get_wtime): runs `iters` SpMVs on `stream` and returns the
- * summed device time of the SpMV KERNEL alone (kernel_ms, CUDA events placed
- * directly around each kernel launch) and of the whole loop including the y
- * initialisation (total_ms). Synchronises the stream. */
+ * loop with omp_get_wtime): runs `iters` SpMVs back to back on `stream` between
+ * two CUDA events (total_ms: y initialisation + kernel, summed over the loop),
+ * then the y initialisation alone the same way; kernel_ms = total_ms minus
+ * that, i.e. the summed device time of the SpMV KERNEL, which by construction
+ * cannot exceed the step time. Synchronises the stream; y = A x on return. */
 int cfs_cuda_spmv_timed(cfs_mat_t m, void *y_dev, const void *x_dev,
                         void *stream, int iters, float *total_ms,
                         float *kernel_ms);

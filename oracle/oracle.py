@@ -305,12 +305,18 @@ def run_ref_dump_csr(input_spec, P, precision, xseed, out_path, tuning="A"):
     return read_dump(out_path)
 
 
-def run_ref_bench(input_spec, P, precision, xseed, loops, timeout=None):
+def run_ref_bench(input_spec, P, precision, xseed, loops, timeout=None,
+                  warmup=-1, y_out=None):
+    """times the compiled reference's SpDMV (ref_tool bench); warmup = -1 is
+    the reference's own loops / 2; y_out: file that receives its y (raw)"""
     import json
     env = dict(os.environ)
     env.setdefault("OMP_PROC_BIND", "close")
-    out = subprocess.run([REF_TOOL, "bench", input_spec, str(P), precision,
-                          str(xseed), str(loops)], env=env, check=True,
+    cmd = [REF_TOOL, "bench", input_spec, str(P), precision, str(xseed),
+           str(loops), str(warmup)]
+    if y_out:
+        cmd.append(y_out)
+    out = subprocess.run(cmd, env=env, check=True,
                          capture_output=True, text=True, timeout=timeout)
     for line in out.stdout.splitlines():
         if line.startswith("{"):

@@ -20,7 +20,8 @@
 //
 //   <input> is  mtx:<file.mtx>              (file ctor, csr_matrix.tpp:9)
 //           or  csr:<file.bin>              (array ctor, csr_matrix.tpp:114)
-//           or  gen:lap7:nx:ny:nz | gen:lap27:nx:ny:nz
+//           or  gen:lap7:nx:ny:nz[:seed] | gen:lap27:nx:ny:nz[:seed]
+//               (seed != 0: one coefficient per edge, see cfs_gen.h)
 //               | gen:banded:nrows:bw:per_row_x16:seed      (array ctor)
 //
 // The metadata of the reference is private (csr_matrix.hpp:77-124); this tool
@@ -144,8 +145,9 @@ void load_csr_bin(const std::string &path, HostCsr &m) {
 void generate(const std::vector<std::string> &a, HostCsr &m) {
   cfs_gen_spec g;
   if (a[1] == "lap7" || a[1] == "lap27")
-    g = cfs_gen_laplacian(a[1] == "lap7" ? 7 : 27, atoi(a[2].c_str()),
-                          atoi(a[3].c_str()), atoi(a[4].c_str()));
+    g = cfs_gen_laplacian_seeded(
+        a[1] == "lap7" ? 7 : 27, atoi(a[2].c_str()), atoi(a[3].c_str()),
+        atoi(a[4].c_str()), a.size() > 5 ? strtoull(a[5].c_str(), 0, 10) : 0);
   else if (a[1] == "banded")
     g = cfs_gen_banded(atoll(a[2].c_str()), atoi(a[3].c_str()),
                        atoi(a[4].c_str()), strtoull(a[5].c_str(), 0, 10));
@@ -330,7 +332,8 @@ int do_dump_csr(const std::string &input, int P, uint64_t xseed,
 }
 
 template <typename V>
-int do_bench(const std::string &input, int P, uint64_t xseed, size_t loops) {
+int do_bench(const std::string &input, int P, uint64_t xseed, size_t loops,
+             long warmup, const char *y_out) {
   double t0 = omp_get_wtime();
   Run<V> r;
   r.open(input);
@@ -349,7 +352,9 @@ int do_bench(const std::string &input, int P, uint64_t xseed, size_t loops) {
   t0 = omp_get_wtime();
   SpDMV<int, V> spdmv(r.A);
   double preproc = omp_get_wtime() - t0;
-  for (size_t i = 0; i < loops / 2; ++i) // warm-up, bench_spmv_mmf.cpp:154
+  // warm-up: loops / 2 like bench_spmv_mmf.cpp:154 unless the caller says
+  const size_t nwarm = warmup >= 0 ? (size_t)warmup : loops / 2;
+  for (size_t i = 0; i < nwarm; ++i)
     spdmv(y, M, x, N);
   std::vector<double> per_step(loops);
   t0 = omp_get_wtime();
@@ -367,10 +372,18 @@ int do_bench(const std::string &input, int P, uint64_t xseed, size_t loops) {
          "\"threads\": %d, \"loops\": %zu, \"load_s\": %.6f, "
          "\"preproc_s\": %.6f, \"t_spmv_s\": %.9f, \"t_spmv_min_s\": %.9f, "
          "\"gflops\": %.6f, \"ncolors\": %d, \"size_bytes\": %zu, "
-         "\"dtype\": \"%s\", \"ysum\": %.17g}\n",
+         "\"dtype\": \"%s\", \"ysum\": %.17g, \"warmup\": %zu}\n",
          M, nnz_full, P, loops, t_load, preproc, total / loops, per_step[0],
          (double)loops * 2.0 * nnz_full * 1e-9 / total, r.csr->ncolors_,
-         r.A->size(), sizeof(V) == 8 ? "f64" : "f32", ysum);
+         r.A->size(), sizeof(V) == 8 ? "f64" : "f32", ysum, nwarm);
+  if (y_out && y_out[0]) { // the reference's y, raw, for full-size parity
+    FILE *f = fopen(y_out, "wb");
+    if (!f || fwrite(y, sizeof(V), M, f) != (size_t)M) {
+      perror(y_out);
+      return 2;
+    }
+    fclose(f);
+  }
   delete r.A;
   internal_free(x);
   internal_free(y);
@@ -382,7 +395,8 @@ int do_bench(const std::string &input, int P, uint64_t xseed, size_t loops) {
 int main(int argc, char **argv) {
   if (argc < 7) {
     fprintf(stderr,
-            "usage: %s dump|bench <input> <P> <d|s> <xseed> <out.bin|loops>\n",
+            "usage: %s dump|bench <input> <P> <d|s> <xseed> <out.bin|loops> "
+            "[bench: warmup (-1 = loops/2)] [bench: y_out.bin]\n",
             argv[0]);
     return 2;
   }
@@ -400,8 +414,13 @@ int main(int argc, char **argv) {
     return dp ? do_dump_csr<double>(input, P, xseed, argv[6], aggressive)
               : do_dump_csr<float>(input, P, xseed, argv[6], aggressive);
   }
-  if (cmd == "bench")
-    return dp ? do_bench<double>(input, P, xseed, (size_t)atoll(argv[6]))
-              : do_bench<float>(input, P, xseed, (size_t)atoll(argv[6]));
+  if (cmd == "bench") {
+    const long warmup = argc > 7 ? atol(argv[7]) : -1;
+    const char *y_out = argc > 8 ? argv[8] : nullptr;
+    return dp ? do_bench<double>(input, P, xseed, (size_t)atoll(argv[6]),
+                                 warmup, y_out)
+              : do_bench<float>(input, P, xseed, (size_t)atoll(argv[6]),
+                                warmup, y_out);
+  }
   return 2;
 }
