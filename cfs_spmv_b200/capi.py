@@ -41,6 +41,8 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_spmv_halo_dot_async", "cfs_cuda_cg_update_xr",
     "cfs_cuda_cg_update_p",
     "cfs_cuda_matrix_export",
+    "cfs_cuda_multi_create", "cfs_cuda_multi_tune", "cfs_cuda_multi_spmv",
+    "cfs_cuda_multi_info", "cfs_cuda_multi_destroy",
     "cfs_gen_host_count", "cfs_gen_host_fill", "cfs_gen_host_x",
     "cfs_cuda_gen_count", "cfs_cuda_gen_fill", "cfs_cuda_gen_x",
 )
@@ -109,6 +111,19 @@ class MatrixInfo(ctypes.Structure):
 
 
 _lib = None
+MULTI_MAX_GPUS = 16
+
+
+class MultiInfo(ctypes.Structure):
+    """cfs_multi_info of include/cfs_cuda.h"""
+    _fields_ = [("ngpus", ctypes.c_int32), ("fused_halo", ctypes.c_int32),
+                ("nrows", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("nnz_full", ctypes.c_int64), ("nnz_low", ctypes.c_int64),
+                ("device", ctypes.c_int32 * MULTI_MAX_GPUS),
+                ("row_begin", ctypes.c_int32 * MULTI_MAX_GPUS),
+                ("row_end", ctypes.c_int32 * MULTI_MAX_GPUS),
+                ("halo_begin", ctypes.c_int32 * MULTI_MAX_GPUS),
+                ("shard_nnz_low", ctypes.c_int64 * MULTI_MAX_GPUS)]
 
 
 class MmfText(ctypes.Structure):
@@ -204,6 +219,14 @@ def lib():
                                       ctypes.POINTER(ctypes.c_float)]
     L.cfs_cuda_matrix_export.argtypes = [vp, ctypes.c_int, vp, sz,
                                          ctypes.POINTER(sz)]
+    L.cfs_cuda_multi_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int,
+                                        ctypes.c_int, i32, vp, vp, vp,
+                                        ctypes.c_int]
+    L.cfs_cuda_multi_tune.argtypes = [vp]
+    L.cfs_cuda_multi_spmv.argtypes = [vp, vp, vp]
+    L.cfs_cuda_multi_info.argtypes = [vp, ctypes.POINTER(MultiInfo)]
+    L.cfs_cuda_multi_destroy.argtypes = [vp]
+    L.cfs_cuda_multi_destroy.restype = None
     L.cfs_cuda_cg_solve.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_double,
                                     ctypes.POINTER(CgResult), vp, ctypes.c_int]
     L.cfs_cuda_spmv_halo_dot_async.argtypes = [vp, vp, vp, vp, ctypes.c_int,
@@ -417,6 +440,51 @@ class Matrix:
     def close(self):
         if self._h:
             lib().cfs_cuda_matrix_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiMatrix:
+    """cfs_multi_t: a symmetric matrix cut into row shards over the GPUs of
+    this process (what the C++ layer does under CFS_NUM_GPUS > 1)"""
+
+    def __init__(self, rowptr, colind, values, ngpus, first_device=0):
+        self._h = ctypes.c_void_p()
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        colind = np.ascontiguousarray(colind, np.int32)
+        values = np.ascontiguousarray(values)
+        assert values.dtype in (np.float32, np.float64)
+        self.dtype = values.dtype
+        check(lib().cfs_cuda_multi_create(
+            ctypes.byref(self._h), ngpus, first_device, len(rowptr) - 1,
+            _ptr(rowptr), _ptr(colind), _ptr(values),
+            int(values.dtype == np.float64)))
+        check(lib().cfs_cuda_multi_tune(self._h))
+
+    def info(self):
+        mi = MultiInfo()
+        check(lib().cfs_cuda_multi_info(self._h, ctypes.byref(mi)))
+        g = mi.ngpus
+        return {"ngpus": g, "fused_halo": mi.fused_halo, "nrows": mi.nrows,
+                "nnz_full": mi.nnz_full, "nnz_low": mi.nnz_low,
+                "device": list(mi.device[:g]),
+                "row_begin": list(mi.row_begin[:g]),
+                "row_end": list(mi.row_end[:g]),
+                "halo_begin": list(mi.halo_begin[:g]),
+                "shard_nnz_low": list(mi.shard_nnz_low[:g])}
+
+    def spmv(self, y, x):
+        check(lib().cfs_cuda_multi_spmv(self._h, _ptr(y), _ptr(x)))
+        return y
+
+    def close(self):
+        if self._h:
+            lib().cfs_cuda_multi_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

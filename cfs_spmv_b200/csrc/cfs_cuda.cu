@@ -192,6 +192,10 @@ static int set_option_checked(const char *key, long long value) {
     g_options.csr_layout = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "keep_layouts") && (value == 0 || value == 1)) {
+    g_options.keep_layouts = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "reg_blocks") && (value == 16 || value == 12)) {
     g_options.reg_blocks = (int)value;
     return CFS_OK;
@@ -560,32 +564,7 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
       clock_gettime(CLOCK_MONOTONIC, &ts);
       return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     };
-    double t0 = now();
-    auto lap = [&](const char *what) {
-      if (!report)
-        return;
-      const double t1 = now();
-      fprintf(stderr, "[tune] %-22s %8.2f ms\n", what, t1 - t0);
-      t0 = t1;
-    };
-    CFS_TRY(build_lower(m, m->stream));
-    lap("lower triangle");
-    CFS_TRY(build_layout(m, m->stream));
-    lap("sliced layout");
-    CFS_TRY(build_windows(m, m->stream));
-    lap("windows (variant 4)");
-    CFS_TRY(build_compressed_cols(m, m->stream));
-    lap("index compression");
-    CFS_TRY(build_tiles6(m, m->stream));
-    lap("transposed tiles");
-    CFS_TRY(build_value_index(m, m->stream));
-    lap("value index");
-    CFS_TRY(build_hubs(m, m->stream));
-    lap("hub columns");
-    CFS_TRY(build_pipeline_plan(m, m->stream));
-    lap("pipeline plan");
-    // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
-    m->row_split.assign((size_t)nparts + 1, 0);
+    // partition count first: an invalid one must not cost a layout build
     if (nparts > 1) {
       if (m->sharded) {
         set_error("reference-compatible metadata (nparts > 1) is defined on "
@@ -599,6 +578,46 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
                   nparts, m->nrows);
         return CFS_ERR_INVALID;
       }
+    }
+    // Layouts of kernels that are not the selected one (variants 1 / 2 / 4: the
+    // uncompressed column stream, window slots, tile records) are built and
+    // kept only for small matrices -- tests switch variants after tune -- or on
+    // request (option keep_layouts): on BASELINE configs[1] they are 0.85 GB
+    // of HBM and 15 % of the tune time for kernels that lost by 1.5-2.8x.
+    const int v_sel = g_options.spmv_variant;
+    const bool keep_all =
+        g_options.keep_layouts || m->nnz_full < (4ll << 20);
+    const bool want_windows = keep_all || v_sel == 2 || v_sel == 3 || v_sel == 4;
+    double t0 = now();
+    auto lap = [&](const char *what) {
+      if (!report)
+        return;
+      const double t1 = now();
+      fprintf(stderr, "[tune] %-22s %8.2f ms\n", what, t1 - t0);
+      t0 = t1;
+    };
+    CFS_TRY(build_lower(m, m->stream));
+    lap("lower triangle");
+    CFS_TRY(build_layout(m, m->stream));
+    lap("sliced layout");
+    if (want_windows) {
+      CFS_TRY(build_windows(m, m->stream));
+      lap("windows (variant 4)");
+    }
+    CFS_TRY(build_compressed_cols(m, m->stream));
+    lap("index compression");
+    CFS_TRY(build_tiles6(m, m->stream));
+    lap("transposed tiles");
+    CFS_TRY(build_value_index(m, m->stream));
+    lap("value index");
+    CFS_TRY(build_hubs(m, m->stream));
+    lap("hub columns");
+    CFS_TRY(build_pipeline_plan(m, m->stream));
+    lap("pipeline plan");
+    // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
+    m->row_split.assign((size_t)nparts + 1, 0);
+    if (nparts > 1) {
+      const long long S = ((m->nrows / nparts - 1) | (kBlkFactor - 1)) + 1;
       for (int t = 0; t < nparts; ++t)
         m->row_split[t] = (int32_t)(t * S);
       m->row_split[nparts] = m->nrows;
@@ -607,6 +626,21 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
         return meta_status;
     } else {
       m->row_split[1] = m->nrows;
+    }
+    if (!keep_all) {
+      // the P = 1 lower CSR (the reference's SymThreadData content) has done
+      // its work: layout, hub columns and metadata are built. Its row pointer
+      // (4 bytes per row) stays for the per-partition counts.
+      m->low_colind.release();
+      m->low_values.release();
+      if (!want_windows) {
+        m->tile_rec.release();
+        m->ntiles = 0;
+      }
+      // regular matrices run from the compressed column stream
+      if (v_sel != 1 && !want_windows && m->ccol.p &&
+          m->nregular * 8 >= m->nslices && m->nhubs == 0)
+        m->sell_col.release();
     }
     // compress_symmetry() frees the full CSR when it owns it (:1700-1706)
     m->own_rowptr.release();
@@ -1109,8 +1143,15 @@ int cfs_cuda_matrix_export(cfs_mat_t m, int what, void *dst, size_t cap,
     return CFS_OK;
   }
   case CFS_META_LOWER_COLIND:
-    return copy_out(m->low_colind.p, (size_t)m->nnz_low, 4, dst, cap, count);
   case CFS_META_LOWER_VALUES:
+    if (!m->low_colind.p && m->nnz_low) {
+      set_error("the lower CSR was released after tune (the kernels read the "
+                "sliced layout): set option keep_layouts=1 before "
+                "cfs_cuda_matrix_tune to export it");
+      return CFS_ERR_STATE;
+    }
+    if (what == CFS_META_LOWER_COLIND)
+      return copy_out(m->low_colind.p, (size_t)m->nnz_low, 4, dst, cap, count);
     return copy_out(m->low_values.p, (size_t)m->nnz_low, vs, dst, cap, count);
   case CFS_META_DIAGONAL:
     return copy_out(m->diagonal.p, N, vs, dst, cap, count);
@@ -1120,6 +1161,12 @@ int cfs_cuda_matrix_export(cfs_mat_t m, int what, void *dst, size_t cap,
     return copy_out(m->vrow_row.p, (size_t)m->nslices * kSliceRows, 4, dst, cap,
                     count);
   case CFS_META_SELL_COL:
+    if (!m->sell_col.p && m->padded_entries) {
+      set_error("the uncompressed column stream was released after tune (the "
+                "selected kernel reads the compressed one): set option "
+                "keep_layouts=1 before cfs_cuda_matrix_tune");
+      return CFS_ERR_STATE;
+    }
     return copy_out(m->sell_col.p, (size_t)m->padded_entries, 4, dst, cap,
                     count);
   case CFS_META_SELL_VAL:

@@ -1,0 +1,330 @@
+// multi.cu -- one process, several GPUs: the reference's thread partitioning
+// (src/runtime.cpp:10-21 picks P, csr_matrix.tpp:404-541 cuts the rows) lifted
+// to the GPUs of one box, behind the C ABI (cfs_cuda_multi_*) so that the C++
+// classes of include/ -- and with them the reference's unmodified
+// bench_spmv_mmf / test_spmv_mmf -- run on CFS_NUM_GPUS devices.
+//
+//   * rows are cut into contiguous, 16-row aligned blocks with about the same
+//     number of stored lower-triangle entries (partition_by_nnz semantics);
+//   * GPU g holds the shard of its rows (cfs_cuda_matrix_create_shard) and
+//     extended local vectors over [halo_begin_g, row_end_g);
+//   * an SpMV: every GPU fetches its piece of x, clears its y, runs its kernel
+//     and hands its rows of y back, each on its own stream; GPUs meet through
+//     events only.
+//     - banded / stencil matrices (every halo inside the block of the GPU
+//       directly below): the kernel reduces its halo contributions straight
+//       into the y of that GPU over NVLink (peer access, RED.sys) -- "fused";
+//     - anything else (R-MAT: a halo reaches down to row 0): every GPU
+//       accumulates into the halo part of its OWN y, and the owners then add
+//       the strips the GPUs above produced for them (a reduce-scatter restricted
+//       to the touched ranges, read over peer access) -- "strips".
+#include <algorithm>
+#include <string.h>
+
+#include "common.cuh"
+
+struct cfs_multi_s {
+  int ngpus = 0;
+  bool is_double = true;
+  bool fused = false;
+  int32_t nrows = 0;
+  int64_t nnz_full = 0, nnz_low = 0;
+  std::vector<int> device;
+  std::vector<int32_t> bound;      // ngpus + 1 row boundaries
+  std::vector<int32_t> halo_begin; // per GPU
+  std::vector<int64_t> shard_nnz_low;
+  std::vector<cfs_mat_t> shard;
+  std::vector<cudaStream_t> stream;
+  std::vector<cudaEvent_t> ready, done; // y cleared + x in / kernel finished
+  std::vector<void *> x_ext, y_ext;     // device buffers over [halo_begin, row_end)
+  size_t vsize() const { return is_double ? 8 : 4; }
+};
+
+namespace cfsb {
+namespace {
+
+// y_own[i] += strip[i] for the rows of this GPU that a GPU above reached into
+template <typename T>
+__global__ void add_strip_kernel(long long n, T *__restrict__ own,
+                                 const T *__restrict__ strip) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    own[i] += strip[i];
+}
+
+// lower-triangle entries of a row of the full CSR (no assumption about the
+// order of its columns, like the reference's extraction, csr_matrix.tpp:1260)
+int64_t lower_count(const int32_t *rowptr, const int32_t *colind, int32_t row) {
+  int64_t n = 0;
+  for (int32_t j = rowptr[row]; j < rowptr[row + 1]; ++j)
+    n += colind[j] < row;
+  return n;
+}
+
+int enable_peer(int from, int to) {
+  if (from == to)
+    return CFS_OK;
+  int can = 0;
+  CFS_CUDA_TRY(cudaDeviceCanAccessPeer(&can, from, to));
+  if (!can) {
+    set_error("GPU %d cannot access GPU %d as a peer", from, to);
+    return CFS_ERR_CUDA;
+  }
+  CFS_CUDA_TRY(cudaSetDevice(from));
+  const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+    return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+  cudaGetLastError();
+  return CFS_OK;
+}
+
+} // namespace
+} // namespace cfsb
+
+using namespace cfsb;
+
+extern "C" {
+
+void cfs_cuda_multi_destroy(cfs_multi_t mm) {
+  if (!mm)
+    return;
+  for (int g = 0; g < (int)mm->shard.size(); ++g) {
+    cudaSetDevice(mm->device[g]);
+    if (g < (int)mm->x_ext.size() && mm->x_ext[g])
+      cudaFree(mm->x_ext[g]);
+    if (g < (int)mm->y_ext.size() && mm->y_ext[g])
+      cudaFree(mm->y_ext[g]);
+    if (g < (int)mm->ready.size() && mm->ready[g])
+      cudaEventDestroy(mm->ready[g]);
+    if (g < (int)mm->done.size() && mm->done[g])
+      cudaEventDestroy(mm->done[g]);
+    if (g < (int)mm->stream.size() && mm->stream[g])
+      cudaStreamDestroy(mm->stream[g]);
+    if (mm->shard[g])
+      cfs_cuda_matrix_destroy(mm->shard[g]);
+  }
+  if (!mm->device.empty())
+    cfs_cuda_init(mm->device[0]);
+  delete mm;
+}
+
+int cfs_cuda_multi_create(cfs_multi_t *out, int ngpus, int first_device,
+                          int32_t nrows, const int32_t *rowptr,
+                          const int32_t *colind, const void *values,
+                          int is_double) {
+  if (!out || ngpus < 1 || nrows < 0 || !rowptr || first_device < 0) {
+    set_error("cfs_cuda_multi_create: bad arguments");
+    return CFS_ERR_INVALID;
+  }
+  int ndev = 0;
+  CFS_TRY(cfs_cuda_device_count(&ndev));
+  if (ndev == 0) {
+    set_error("no CUDA device visible: the B200 path has no CPU fallback");
+    return CFS_ERR_NO_DEVICE;
+  }
+  if (first_device + ngpus > ndev) {
+    set_error("CFS_NUM_GPUS=%d from device %d, but %d device(s) are visible",
+              ngpus, first_device, ndev);
+    return CFS_ERR_INVALID;
+  }
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, rowptr) == cudaSuccess &&
+      at.type == cudaMemoryTypeDevice) {
+    set_error("cfs_cuda_multi_create: the CSR arrays must be host memory (the "
+              "rows are dealt out to the GPUs from there)");
+    return CFS_ERR_INVALID;
+  }
+  cudaGetLastError();
+  if (nrows < 16 * ngpus)
+    ngpus = 1; // nothing to cut
+  cfs_multi_s *mm = new cfs_multi_s;
+  mm->ngpus = ngpus;
+  mm->is_double = is_double != 0;
+  mm->nrows = nrows;
+  mm->nnz_full = rowptr[nrows];
+  for (int g = 0; g < ngpus; ++g)
+    mm->device.push_back(first_device + g);
+  // nnz-balanced, 16-row aligned row blocks over the LOWER triangle (what a
+  // GPU streams): prefix sums of the per-row counts, cut at g / ngpus
+  std::vector<int64_t> prefix((size_t)nrows + 1, 0);
+  for (int32_t i = 0; i < nrows; ++i)
+    prefix[i + 1] = prefix[i] + lower_count(rowptr, colind, i) + 1; // + diagonal
+  mm->nnz_low = prefix[nrows] - nrows;
+  mm->bound.assign((size_t)ngpus + 1, 0);
+  mm->bound[ngpus] = nrows;
+  for (int g = 1; g < ngpus; ++g) {
+    const int64_t target = prefix[nrows] * g / ngpus;
+    int32_t r = (int32_t)(std::lower_bound(prefix.begin(), prefix.end(), target) -
+                          prefix.begin());
+    r = (r + kBlkFactor / 2) / kBlkFactor * kBlkFactor;
+    r = std::min(r, nrows);
+    mm->bound[g] = std::max(r, mm->bound[g - 1]);
+  }
+  const size_t vs = mm->vsize();
+  int status = CFS_OK;
+  mm->shard.assign((size_t)ngpus, nullptr);
+  mm->halo_begin.assign((size_t)ngpus, 0);
+  mm->shard_nnz_low.assign((size_t)ngpus, 0);
+  for (int g = 0; g < ngpus && status == CFS_OK; ++g) {
+    const int32_t b = mm->bound[g], e = mm->bound[g + 1];
+    status = cfs_cuda_init(mm->device[g]);
+    if (status != CFS_OK)
+      break;
+    std::vector<int32_t> local((size_t)(e - b) + 1);
+    for (int32_t i = b; i <= e; ++i)
+      local[i - b] = rowptr[i] - rowptr[b];
+    status = cfs_cuda_matrix_create_shard(
+        &mm->shard[g], nrows, b, e, local.data(), colind + rowptr[b],
+        (const char *)values + (size_t)rowptr[b] * vs, is_double);
+  }
+  if (status != CFS_OK) {
+    cfs_cuda_multi_destroy(mm);
+    return status;
+  }
+  cfs_cuda_init(mm->device[0]); // the process's own device again
+  *out = mm;
+  return CFS_OK;
+}
+
+int cfs_cuda_multi_tune(cfs_multi_t mm) {
+  if (!mm)
+    return CFS_ERR_INVALID;
+  const int G = mm->ngpus;
+  const size_t vs = mm->vsize();
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    CFS_TRY(cfs_cuda_init(mm->device[g]));
+    CFS_TRY(cfs_cuda_matrix_tune(mm->shard[g], 1, CFS_TUNING_AGGRESSIVE));
+    cfs_matrix_info info;
+    CFS_TRY(cfs_cuda_matrix_info(mm->shard[g], &info));
+    mm->halo_begin[g] = info.halo_begin;
+    mm->shard_nnz_low[g] = info.nnz_low;
+  }
+  // fused halo: every halo inside the block of the GPU directly below
+  mm->fused = true;
+  for (int g = 1; g < G; ++g)
+    if (mm->halo_begin[g] < mm->bound[g - 1])
+      mm->fused = false;
+  // who reads whom: g writes into g-1 (fused), or the owners h < g read the
+  // strips of every g whose halo reaches into their rows
+  for (int g = 1; g < G; ++g) {
+    if (mm->fused) {
+      if (mm->halo_begin[g] < mm->bound[g])
+        CFS_TRY(enable_peer(mm->device[g], mm->device[g - 1]));
+    } else {
+      for (int h = 0; h < g; ++h)
+        if (mm->halo_begin[g] < mm->bound[h + 1])
+          CFS_TRY(enable_peer(mm->device[h], mm->device[g]));
+    }
+  }
+  mm->stream.assign((size_t)G, nullptr);
+  mm->ready.assign((size_t)G, nullptr);
+  mm->done.assign((size_t)G, nullptr);
+  mm->x_ext.assign((size_t)G, nullptr);
+  mm->y_ext.assign((size_t)G, nullptr);
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    CFS_CUDA_TRY(cudaStreamCreateWithFlags(&mm->stream[g],
+                                           cudaStreamNonBlocking));
+    CFS_CUDA_TRY(cudaEventCreateWithFlags(&mm->ready[g],
+                                          cudaEventDisableTiming));
+    CFS_CUDA_TRY(cudaEventCreateWithFlags(&mm->done[g],
+                                          cudaEventDisableTiming));
+    const size_t len = (size_t)(mm->bound[g + 1] - mm->halo_begin[g]);
+    CFS_CUDA_TRY(cudaMalloc(&mm->x_ext[g], (len ? len : 1) * vs));
+    CFS_CUDA_TRY(cudaMalloc(&mm->y_ext[g], (len ? len : 1) * vs));
+  }
+  return cfs_cuda_init(mm->device[0]);
+}
+
+int cfs_cuda_multi_spmv(cfs_multi_t mm, void *y, const void *x) {
+  if (!mm || !y || !x)
+    return CFS_ERR_INVALID;
+  if (mm->stream.empty()) {
+    set_error("cfs_cuda_multi_spmv: call cfs_cuda_multi_tune first");
+    return CFS_ERR_STATE;
+  }
+  const int G = mm->ngpus;
+  const size_t vs = mm->vsize();
+  // 1. every GPU: its piece of x in, its y clear
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    const size_t len = (size_t)(mm->bound[g + 1] - mm->halo_begin[g]);
+    CFS_CUDA_TRY(cudaMemcpyAsync(mm->x_ext[g],
+                                 (const char *)x + (size_t)mm->halo_begin[g] * vs,
+                                 len * vs, cudaMemcpyDefault, mm->stream[g]));
+    CFS_CUDA_TRY(cudaMemsetAsync(mm->y_ext[g], 0, len * vs, mm->stream[g]));
+    CFS_CUDA_TRY(cudaEventRecord(mm->ready[g], mm->stream[g]));
+  }
+  // 2. kernels; a fused kernel reduces into the y of the GPU below, which must
+  // be clear by then
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    void *y_lower = nullptr;
+    if (mm->fused && g > 0 && mm->halo_begin[g] < mm->bound[g]) {
+      CFS_CUDA_TRY(cudaStreamWaitEvent(mm->stream[g], mm->ready[g - 1], 0));
+      y_lower = (char *)mm->y_ext[g - 1] - (size_t)mm->halo_begin[g - 1] * vs;
+    }
+    CFS_TRY(cfs_cuda_spmv_shard_async(mm->shard[g], mm->y_ext[g], mm->x_ext[g],
+                                      y_lower, nullptr, nullptr, 1,
+                                      mm->stream[g]));
+    CFS_CUDA_TRY(cudaEventRecord(mm->done[g], mm->stream[g]));
+  }
+  // 3. the rows of y are final once everybody above has contributed
+  for (int h = 0; h < G; ++h) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[h]));
+    const int32_t b = mm->bound[h], e = mm->bound[h + 1];
+    char *own = (char *)mm->y_ext[h] + (size_t)(b - mm->halo_begin[h]) * vs;
+    for (int g = h + 1; g < G; ++g) {
+      const int32_t lo = std::max(mm->halo_begin[g], b);
+      const int32_t hi = std::min(mm->bound[g], e);
+      if (lo >= hi)
+        continue; // g's halo does not reach into the rows of h
+      CFS_CUDA_TRY(cudaStreamWaitEvent(mm->stream[h], mm->done[g], 0));
+      if (mm->fused)
+        continue; // already reduced in place by g's kernel
+      const long long n = hi - lo;
+      const char *strip =
+          (const char *)mm->y_ext[g] + (size_t)(lo - mm->halo_begin[g]) * vs;
+      char *dst = own + (size_t)(lo - b) * vs;
+      const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+      if (mm->is_double)
+        add_strip_kernel<double><<<grid, 256, 0, mm->stream[h]>>>(
+            n, (double *)dst, (const double *)strip);
+      else
+        add_strip_kernel<float><<<grid, 256, 0, mm->stream[h]>>>(
+            n, (float *)dst, (const float *)strip);
+      CFS_CUDA_TRY(cudaGetLastError());
+    }
+    CFS_CUDA_TRY(cudaMemcpyAsync((char *)y + (size_t)b * vs, own,
+                                 (size_t)(e - b) * vs, cudaMemcpyDefault,
+                                 mm->stream[h]));
+  }
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    CFS_CUDA_TRY(cudaStreamSynchronize(mm->stream[g]));
+  }
+  CFS_CUDA_TRY(cudaSetDevice(mm->device[0]));
+  return CFS_OK;
+}
+
+int cfs_cuda_multi_info(cfs_multi_t mm, cfs_multi_info *info) {
+  if (!mm || !info)
+    return CFS_ERR_INVALID;
+  memset(info, 0, sizeof(*info));
+  info->ngpus = mm->ngpus;
+  info->fused_halo = mm->fused ? 1 : 0;
+  info->nrows = mm->nrows;
+  info->nnz_full = mm->nnz_full;
+  info->nnz_low = mm->nnz_low;
+  for (int g = 0; g < mm->ngpus && g < CFS_MULTI_MAX_GPUS; ++g) {
+    info->row_begin[g] = mm->bound[g];
+    info->row_end[g] = mm->bound[g + 1];
+    info->halo_begin[g] = mm->halo_begin[g];
+    info->shard_nnz_low[g] = mm->shard_nnz_low[g];
+    info->device[g] = mm->device[g];
+  }
+  return CFS_OK;
+}
+
+} // extern "C"

@@ -184,6 +184,19 @@ __global__ void __launch_bounds__(kSpmvThreads)
 
 constexpr int kStages = 2; // ring depth of the persistent kernel
 
+// function attributes (dynamic shared memory limits) belong to a device: one
+// process may drive several (multi.cu), so what has been granted is remembered
+// per device
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+  int v[kMaxDevices] = {};
+  int &here() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return v[dev < 0 || dev >= kMaxDevices ? 0 : dev];
+  }
+};
+
 // what only the sharded / ping-pong entry points set: the x vector of the GPU
 // below (virtual base, read over NVLink by the halo kernels) and the vector the
 // row owners clear for the next SpMV
@@ -228,7 +241,8 @@ void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
 
 template <typename T, int MODE>
 int launch_tma(const cfs_matrix_s *m, const T *xb, T *yb, cudaStream_t s) {
-  static int num_sms = 0, max_ctas = 0;
+  static PerDevice sms_of, ctas_of;
+  int &num_sms = sms_of.here(), &max_ctas = ctas_of.here();
   const int smem_bytes = tma::Stage<T>::smem_bytes(kStages);
   auto kernel = tma::sym_spmv_tma_kernel<T, kStages, MODE>;
   if (!num_sms) {
@@ -271,7 +285,8 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   int smem = 0;
   if (!y_lower && (s0 != 0 || s1 != m->nslices) && g_options.pipeline_smem) {
     smem = g_options.pipeline_smem;
-    static int granted = 0;
+    static PerDevice granted_of;
+    int &granted = granted_of.here();
     if (granted < smem) {
       CFS_CUDA_TRY(cudaFuncSetAttribute(
           reg::sym_spmv_reg_kernel<T, false>,
@@ -293,7 +308,8 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
 #define CFS_LAUNCH_BULK(HALO, DOT, YL, DOTP)                                   \
   do {                                                                         \
     auto kernel = reg::sym_spmv_reg_kernel<T, HALO, DOT, 0, false, true>;      \
-    static int granted_bulk = 0; /* per instantiation */                       \
+    static PerDevice granted_of; /* per instantiation */                       \
+    int &granted_bulk = granted_of.here();                                     \
     if (granted_bulk < bulk_smem) {                                            \
       CFS_CUDA_TRY(cudaFuncSetAttribute(                                       \
           kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bulk_smem));    \
@@ -365,7 +381,8 @@ int launch_tile6_as(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   // products of the largest tile (rounded to 8 entries) + its slot offsets
   const int prod_entries = (m->t6_smem_entries + 7) & ~7;
   const int smem = prod_entries * (int)sizeof(T) + (m->t6_max_cols + 2) * 2;
-  static int granted = 0; // per instantiation
+  static PerDevice granted_of; // per instantiation
+  int &granted = granted_of.here();
   if (granted < smem) {
     const int cap = kT6MaxSmemBytes + (kT6MaxCols + 2) * 2;
     CFS_CUDA_TRY(cudaFuncSetAttribute(
@@ -437,6 +454,12 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
     return launch_reg<T>(m, xb, yb, yl, s, s0, s1, ex, dot);
   if (variant == 5 || yl || partial || dot || ex.y_clear)
     variant = 1;
+  if (!m->sell_col.p && m->padded_entries) {
+    set_error("SpMV variant %d needs the uncompressed column stream, which was "
+              "released after tune: set option keep_layouts=1 before "
+              "cfs_cuda_matrix_tune", variant);
+    return CFS_ERR_STATE;
+  }
   if (dot) {
     launch_sell<T, 0>(m, xb, yb, yl, s, s0, s1, ex, dot);
     return CFS_OK;

@@ -148,7 +148,8 @@ CSRMatrix<IndexT, ValueT>::CSRMatrix(const string &filename, Platform platform,
                                      bool symmetric, bool hybrid)
     : platform_(platform), hybrid_(hybrid), owns_data_(true), tuned_(false),
       nparts_((int)get_num_threads()), rowptr_(nullptr), colind_(nullptr),
-      values_(nullptr), device_(nullptr), host_csr_pending_(false) {
+      values_(nullptr), device_(nullptr), multi_(nullptr),
+      ngpus_(get_num_gpus()), host_csr_pending_(false) {
   if (ingest_on_gpu(filename, symmetric)) {
 #ifdef _LOG_INFO
     if (!symmetric)
@@ -213,7 +214,8 @@ CSRMatrix<IndexT, ValueT>::CSRMatrix(IndexT *rowptr, IndexT *colind,
     : platform_(platform), nrows_(nrows), ncols_(ncols), nnz_(rowptr[nrows]),
       symmetric_(symmetric), hybrid_(hybrid), owns_data_(false), tuned_(false),
       nparts_((int)get_num_threads()), rowptr_(rowptr), colind_(colind),
-      values_(values), device_(nullptr), host_csr_pending_(false) {
+      values_(values), device_(nullptr), multi_(nullptr),
+      ngpus_(get_num_gpus()), host_csr_pending_(false) {
   if (nparts_ == 1)
     hybrid_ = false;
 }
@@ -235,10 +237,20 @@ CSRMatrix<IndexT, ValueT>::~CSRMatrix() {
   release_host_csr();
   if (device_)
     cfs_cuda_matrix_destroy(device_);
+  if (multi_)
+    cfs_cuda_multi_destroy(multi_);
 }
 
 template <typename IndexT, typename ValueT>
 size_t CSRMatrix<IndexT, ValueT>::size() const {
+  if (multi_) {
+    // the P = 1 formula of size() (csr_matrix.tpp:191-228) over all shards
+    cfs_multi_info info;
+    fatal_unless_ok(cfs_cuda_multi_info(multi_, &info), "cfs_cuda_multi_info");
+    return ((size_t)info.nrows + 1) * sizeof(IndexT) +
+           (size_t)info.nnz_low * (sizeof(IndexT) + sizeof(ValueT)) +
+           (size_t)info.nrows * sizeof(ValueT);
+  }
   if (device_) {
     cfs_matrix_info info;
     fatal_unless_ok(cfs_cuda_matrix_info(device_, &info),
@@ -257,6 +269,32 @@ bool CSRMatrix<IndexT, ValueT>::tune(Kernel, Tuning t) {
     return true;
   bind_device_once();
   const int is_double = std::is_same<ValueT, double>::value ? 1 : 0;
+  if (symmetric_ && ngpus_ > 1) {
+    // one process, CFS_NUM_GPUS devices: rows dealt out from the host CSR
+    fetch_host_csr();
+    if (device_) { // a GPU-ingested file: its single-GPU CSR has been fetched
+      cfs_cuda_matrix_destroy(device_);
+      device_ = nullptr;
+    }
+    fatal_unless_ok(cfs_cuda_multi_create(&multi_, ngpus_, get_gpu_device(),
+                                          nrows_, (const int32_t *)rowptr_,
+                                          (const int32_t *)colind_, values_,
+                                          is_double),
+                    "cfs_cuda_multi_create");
+    fatal_unless_ok(cfs_cuda_multi_tune(multi_), "cfs_cuda_multi_tune");
+#ifdef _LOG_INFO
+    cfs_multi_info mi;
+    cfs_cuda_multi_info(multi_, &mi);
+    cout << "[INFO]: " << mi.ngpus << " GPUs, nnz-balanced row blocks, "
+         << (mi.fused_halo ? "halo reduced over NVLink inside the kernel"
+                           : "halo strips added by the owners")
+         << endl;
+#endif
+    if (owns_data_)
+      release_host_csr();
+    tuned_ = true;
+    return true;
+  }
   if (!device_) // a GPU-ingested file is there already
     fatal_unless_ok(cfs_cuda_matrix_create(&device_, nrows_, ncols_,
                                            (const int32_t *)rowptr_,
@@ -296,6 +334,10 @@ void CSRMatrix<IndexT, ValueT>::dense_vector_multiply(
   if (!tuned_) {
     cout << "[ERROR]: dense_vector_multiply() before tune()" << endl;
     exit(1);
+  }
+  if (multi_) {
+    fatal_unless_ok(cfs_cuda_multi_spmv(multi_, y, x), "cfs_cuda_multi_spmv");
+    return;
   }
   fatal_unless_ok(cfs_cuda_spmv(device_, y, x), "cfs_cuda_spmv");
 }

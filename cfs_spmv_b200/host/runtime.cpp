@@ -20,6 +20,11 @@ size_t get_num_threads() { return (size_t)env_int("CFS_NUM_THREADS", 1); }
 
 int get_gpu_device() { return env_int("CFS_GPU_DEVICE", 0); }
 
+int get_num_gpus() {
+  const int n = env_int("CFS_NUM_GPUS", 1);
+  return n < 1 ? 1 : n;
+}
+
 void setaffinity_oncpu(unsigned int cpu) {
   cpu_set_t mask;
   CPU_ZERO(&mask);

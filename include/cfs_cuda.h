@@ -61,7 +61,18 @@ const char *cfs_cuda_version(void);
  *                    compressed index stream + shuffle-merged REDs (default; on
  *                    irregular matrices with bounded column windows it hands
  *                    over to 6); 6 = transposed term transposed through shared
- *                    memory
+ *                    memory; 7 = 5 with every slice's value block staged in
+ *                    shared memory by one TMA bulk copy per warp
+ *   "l2_prefetch"    0/1  variant 5 with streamed values: one L2 prefetch per
+ *                    128-byte line of the slice's value block up front
+ *   "reg_blocks"     16/12  resident 128-thread CTAs per SM variant 5 asks for
+ *   "keep_layouts"   0/1  (tune time) keep the layouts of the kernel variants
+ *                    that are not selected and the P = 1 lower CSR; default:
+ *                    only for matrices below 4 M entries. Needed to switch
+ *                    spmv_variant after tune or to export CFS_META_LOWER_* /
+ *                    CFS_META_SELL_COL on a large matrix
+ *   "managed_prefetch", "managed_advise"   unified-memory vectors, see
+ *                    cfs_cuda_host_alloc
  *   "tile6"          0/1  allow variant 6 (read at tune and at launch time)
  *   "value_index"    0/1  dictionary-coded values where the lower triangle has
  *                    <= 256 distinct values (lossless; tune and launch time)
@@ -258,6 +269,40 @@ int cfs_cuda_spmv_halo_async(cfs_mat_t m, void *y_dev, const void *x_dev,
 int cfs_cuda_spmv_shard_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                               void *y_lower_base, const void *x_lower_base,
                               void *y_clear, int y_is_zero, void *stream);
+
+/* ---- one process, several GPUs: replaces the role of get_num_threads
+ * (src/runtime.cpp:10-21) + partition_by_nnz (csr_matrix.tpp:438-541) for the
+ * GPUs of one box. The C++ layer takes this path when CFS_NUM_GPUS > 1
+ * (include/utils/runtime.hpp: get_num_gpus): the rows of a symmetric matrix are
+ * cut into ngpus contiguous, 16-row aligned blocks with about the same number
+ * of stored lower-triangle entries, GPU first_device + g holds the shard of
+ * block g, and cfs_cuda_multi_spmv computes y = A x with HOST, managed or
+ * device vectors of full length: every GPU fetches the piece of x it needs,
+ * runs its kernel and writes its rows of y, concurrently. Contributions that
+ * cross a block boundary are reduced straight into the y of the GPU below over
+ * NVLink peer access when every halo lies inside that one block (banded /
+ * stencil matrices, fused_halo = 1), else the owners add the strips the GPUs
+ * above produced for them (a reduce-scatter restricted to the touched ranges;
+ * R-MAT). rowptr / colind / values: FULL CSR in host memory, borrowed during
+ * the call only. */
+typedef struct cfs_multi_s *cfs_multi_t;
+#define CFS_MULTI_MAX_GPUS 16
+typedef struct cfs_multi_info {
+  int32_t ngpus, fused_halo, nrows, reserved;
+  int64_t nnz_full, nnz_low;
+  int32_t device[CFS_MULTI_MAX_GPUS];
+  int32_t row_begin[CFS_MULTI_MAX_GPUS], row_end[CFS_MULTI_MAX_GPUS];
+  int32_t halo_begin[CFS_MULTI_MAX_GPUS];
+  int64_t shard_nnz_low[CFS_MULTI_MAX_GPUS];
+} cfs_multi_info;
+int cfs_cuda_multi_create(cfs_multi_t *out, int ngpus, int first_device,
+                          int32_t nrows, const int32_t *rowptr,
+                          const int32_t *colind, const void *values,
+                          int is_double);
+int cfs_cuda_multi_tune(cfs_multi_t mm);
+int cfs_cuda_multi_spmv(cfs_multi_t mm, void *y, const void *x);
+int cfs_cuda_multi_info(cfs_multi_t mm, cfs_multi_info *info);
+void cfs_cuda_multi_destroy(cfs_multi_t mm);
 
 /* ---- conjugate gradients on the device: solves A x = b
  * for a tuned symmetric positive definite matrix with the SpMV above as its

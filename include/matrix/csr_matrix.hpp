@@ -7,6 +7,9 @@
 // present (cfs_cuda_matrix_create_from_mmf): its full CSR then lives in HBM
 // and the host copy behind rowptr() / colind() / values() is only made when
 // one of them is called.
+// With CFS_NUM_GPUS > 1 a symmetric matrix is cut into nnz-balanced row blocks,
+// one per GPU of the box (cfs_cuda_multi_*, the role of get_num_threads +
+// partition_by_nnz in the reference), behind the same two calls.
 #ifndef CSR_MATRIX_HPP
 #define CSR_MATRIX_HPP
 
@@ -24,7 +27,8 @@
 
 using namespace std;
 
-struct cfs_matrix_s; // opaque handle of the C ABI
+struct cfs_matrix_s; // opaque handles of the C ABI
+struct cfs_multi_s;
 
 namespace cfs {
 
@@ -88,6 +92,8 @@ private:
   mutable IndexT *colind_;
   mutable ValueT *values_;
   cfs_matrix_s *device_;
+  cfs_multi_s *multi_; // CFS_NUM_GPUS > 1: row shards over the GPUs of the box
+  int ngpus_;          // CFS_NUM_GPUS when the object was built
   mutable bool host_csr_pending_; // the full CSR is in HBM only (GPU ingest)
 
   void release_host_csr();

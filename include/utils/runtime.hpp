@@ -20,8 +20,13 @@ const int MaxThreads = 96;
 size_t get_num_threads();
 // Pins the calling host thread (reference src/runtime.cpp:23-35).
 void setaffinity_oncpu(unsigned int cpu);
-// CFS_GPU_DEVICE, default 0: the GPU this process drives.
+// CFS_GPU_DEVICE, default 0: the (first) GPU this process drives.
 int get_gpu_device();
+// CFS_NUM_GPUS, default 1: GPUs a symmetric matrix is spread over -- what
+// CFS_NUM_THREADS is to the reference's host threads (src/runtime.cpp:10-21):
+// rows are cut into that many nnz-balanced blocks, one per GPU, from
+// CFS_GPU_DEVICE upwards.
+int get_num_gpus();
 
 } // namespace runtime
 } // namespace util

@@ -14,6 +14,7 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 7
     is_double = (sys.argv[3] if len(sys.argv) > 3 else "d") == "d"
     capi.init(0)
+    capi.set_option("keep_layouts", 1)  # variants are switched after tune
     spec = capi.GenSpec.laplacian(27, n, n, n, seed)
     N = spec.nrows
     rp, ci, v = capi.gen_device_csr(spec, is_double=is_double)
