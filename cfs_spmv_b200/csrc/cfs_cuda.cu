@@ -192,6 +192,10 @@ static int set_option_checked(const char *key, long long value) {
     g_options.csr_layout = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "deterministic") && (value == 0 || value == 1)) {
+    g_options.deterministic = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "keep_layouts") && (value == 0 || value == 1)) {
     g_options.keep_layouts = (int)value;
     return CFS_OK;
@@ -974,7 +978,7 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   classify(x, &kx, &px, &mx);
   classify(y, &ky, &py, &my);
   if (kx == kPtrHost && ky == kPtrHost && m->symmetric && !m->stages.empty() &&
-      g_options.pipeline)
+      g_options.pipeline && !g_options.deterministic)
     return spmv_host_pipelined(m, y, x, px && py);
   // a call on unified memory that took far longer than the matrix can explain
   // ran into page faults: the host touches the vectors between calls, so the

@@ -100,6 +100,7 @@ struct Options {
   int rechunk_pct = 130; // ... as a percentage of the mean row length
   int rechunk = 1;     // ragged matrices: virtual rows of ~1.3 x the mean row length
   int tile6 = 1;      // variant 6 where it applies (bounded column windows)
+  int deterministic = 0; // y bitwise reproducible: integer reductions (det.cu)
   int keep_layouts = 0; // keep the layouts of non-selected kernel variants (tune time)
   int reg_blocks = 16; // variant 5: resident 128-thread CTAs per SM asked for (16 or 12)
   int l2_prefetch = 1; // variant 5, streamed values: prefetch.global.L2 per slice
@@ -160,6 +161,13 @@ struct cfs_matrix_s {
   // execution layout: sliced ELL over virtual rows
   int64_t nvrows = 0, nslices = 0, padded_entries = 0;
   int max_slice_steps = 0; // widest slice (steps of 32 entries)
+  int max_row_nnz_full = 0; // longest row of the FULL matrix (terms one y gets)
+  // deterministic mode (det.cu): 64-bit fixed-point y, {|A|max bits, |x|max
+  // bits} and {scale, 1/scale}; all built on first use
+  mutable cfsb::DevArray<long long> det_acc;
+  mutable cfsb::DevArray<unsigned long long> det_max;
+  mutable cfsb::DevArray<double> det_scale;
+  mutable bool det_amax_done = false;
   int64_t sort_window = 0; // 0: natural order; else rows sorted by length in windows
   cfsb::DevArray<int32_t> slice_ptr;  // nslices+1, units of 32 entries
   cfsb::DevArray<int32_t> vrow_row;   // nslices*32
@@ -276,6 +284,9 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                     long long slice1 = -1, double *xdoty = nullptr,
                     const void *x_lower_base = nullptr,
                     void *y_clear = nullptr);
+// deterministic mode (det.cu): before / after the kernel
+int det_prepare(const cfs_matrix_s *m, const void *x_ext, cudaStream_t s);
+int det_finish(const cfs_matrix_s *m, void *y_ext, cudaStream_t s);
 // host-vector pipeline plan (preproc.cu)
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,

@@ -31,10 +31,12 @@ __global__ void count_lower_kernel(int nrows, int row_begin,
                                    const int *__restrict__ colind,
                                    int *__restrict__ low_count,
                                    int *__restrict__ min_col,
-                                   unsigned long long *__restrict__ ndiag) {
+                                   unsigned long long *__restrict__ ndiag,
+                                   int *__restrict__ max_len) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int my_min = INT_MAX, my_diag = 0;
+  int my_min = INT_MAX, my_diag = 0, my_len = 0;
   if (i < nrows) {
+    my_len = rowptr[i + 1] - rowptr[i];
     const int grow = row_begin + i;
     int cnt = 0;
     for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
@@ -51,9 +53,12 @@ __global__ void count_lower_kernel(int nrows, int row_begin,
   int bmin = Reduce(tmp).Reduce(my_min, cub::Min());
   __syncthreads();
   int bdiag = Reduce(tmp).Sum(my_diag);
+  __syncthreads();
+  int blen = Reduce(tmp).Reduce(my_len, cub::Max());
   if (threadIdx.x == 0) {
     atomicMin(min_col, bmin);
     atomicAdd(ndiag, (unsigned long long)bdiag);
+    atomicMax(max_len, blen);
   }
 }
 
@@ -289,10 +294,12 @@ int build_lower(cfs_matrix_s *m, cudaStream_t s) {
   DevArray<int> counts; // n+1 so that the scan yields rowptr[n]
   CFS_TRY(counts.alloc((size_t)n + 1));
   CFS_CUDA_TRY(cudaMemsetAsync(counts.p, 0, ((size_t)n + 1) * 4, s));
-  DevArray<int> min_col;
+  DevArray<int> min_col, max_len;
   DevArray<unsigned long long> ndiag;
   CFS_TRY(min_col.alloc(1));
+  CFS_TRY(max_len.alloc(1));
   CFS_TRY(ndiag.alloc(1));
+  CFS_CUDA_TRY(cudaMemsetAsync(max_len.p, 0, 4, s));
   const int init_min = m->row_begin;
   CFS_CUDA_TRY(cudaMemcpyAsync(min_col.p, &init_min, 4, cudaMemcpyHostToDevice,
                                s));
@@ -300,7 +307,7 @@ int build_lower(cfs_matrix_s *m, cudaStream_t s) {
   if (n > 0)
     count_lower_kernel<<<blocks_for(n), kThreads, 0, s>>>(
         n, m->row_begin, m->csr_rowptr, m->csr_colind, counts.p, min_col.p,
-        ndiag.p);
+        ndiag.p, max_len.p);
   CFS_CUDA_TRY(cudaGetLastError());
   CFS_TRY(m->low_rowptr.alloc((size_t)n + 1));
   CFS_TRY(exclusive_scan_i32(counts.p, m->low_rowptr.p, (size_t)n + 1, s));
@@ -310,6 +317,8 @@ int build_lower(cfs_matrix_s *m, cudaStream_t s) {
                           cudaMemcpyDeviceToHost));
   CFS_CUDA_TRY(cudaMemcpy(&hmin, min_col.p, 4, cudaMemcpyDeviceToHost));
   CFS_CUDA_TRY(cudaMemcpy(&hdiag, ndiag.p, 8, cudaMemcpyDeviceToHost));
+  CFS_CUDA_TRY(cudaMemcpy(&m->max_row_nnz_full, max_len.p, 4,
+                          cudaMemcpyDeviceToHost));
   m->nnz_low = nlow;
   m->nnz_diag = (int64_t)hdiag;
   // multiple of 32 columns: keeps every 32-column window block 16-byte

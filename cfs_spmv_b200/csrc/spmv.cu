@@ -62,7 +62,8 @@ constexpr int kUnroll = 4;
 //
 // x and y are "virtual base" pointers: indexed by GLOBAL row/column id (for a
 // shard they point halo_begin elements before the extended local vector).
-template <typename T, int MODE, bool HALO, bool HUBS, bool DOT = false>
+template <typename T, int MODE, bool HALO, bool HUBS, bool DOT = false,
+          bool DET = false>
 __global__ void __launch_bounds__(kSpmvThreads)
     sym_spmv_sell_kernel(long long slice_begin, long long slice_end,
                          int row_begin,
@@ -74,12 +75,20 @@ __global__ void __launch_bounds__(kSpmvThreads)
                          const T *__restrict__ x, T *__restrict__ y,
                          T *__restrict__ y_lower, double *__restrict__ dot,
                          const T *__restrict__ x_lower,
-                         T *__restrict__ y_clear) {
+                         T *__restrict__ y_clear, long long *__restrict__ yq,
+                         const double *__restrict__ qscale) {
   const int lane = threadIdx.x & 31;
   const long long s =
       slice_begin + ((blockIdx.x * (long long)kSpmvThreads + threadIdx.x) >> 5);
   if (s >= slice_end)
     return;
+  const double scale = DET ? *qscale : 0.0; // deterministic mode, spmv_tma.cuh
+  auto emit = [&](int col, T v) {
+    if (DET)
+      tma::det_add(yq + col, (double)v, scale);
+    else
+      tma::y_add<HALO>(y, y_lower, row_begin, col, v);
+  };
   const int tag = vrow_row[s * kSliceRows + lane];
   const bool active = tag >= 0;
   const int row = tag & kVrowRowMask;
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(kSpmvThreads)
         if (MODE & 1)
           acc += a[u] * xr;
         else if (!hub[u])
-          tma::y_add<HALO>(y, y_lower, row_begin, c[u], a[u] * xr);
+          emit(c[u], a[u] * xr);
       }
     }
     cp += kUnroll * kSliceRows;
@@ -139,13 +148,16 @@ __global__ void __launch_bounds__(kSpmvThreads)
       acc += a * ((MODE & 2) ? xr
                              : tma::x_at<HALO>(x, x_lower, row_begin, c));
       if (!(MODE & 1) && !hub)
-        tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
+        emit(c, a * xr);
     }
     cp += kSliceRows;
     vp += kSliceRows;
   }
   if (active) {
-    tma::red_add(y + row, acc);
+    if (DET)
+      tma::det_add(yq + row, (double)acc, scale);
+    else
+      tma::red_add(y + row, acc);
     if (y_clear && !(tag & kVrowCont)) // see spmv_reg.cuh
       y_clear[row] = T(0);
   }
@@ -203,6 +215,8 @@ struct PerDevice {
 struct Extras {
   const void *x_lower = nullptr;
   void *y_clear = nullptr;
+  long long *yq = nullptr;        // deterministic mode: 64-bit fixed-point y
+  const double *qscale = nullptr; // ... and its scale (device)
 };
 
 template <typename T, int MODE>
@@ -220,7 +234,15 @@ void launch_sell(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
   sym_spmv_sell_kernel<T, M, HALO, HUBS, DOT><<<grid, kSpmvThreads, 0, s>>>(   \
       s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, COLS,               \
       (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, YL, DOTP,    \
-      xl, yc)
+      xl, yc, nullptr, nullptr)
+  if (ex.yq) { // deterministic mode: one kernel, integer reductions
+    sym_spmv_sell_kernel<T, 0, false, false, false, true>
+        <<<grid, kSpmvThreads, 0, s>>>(
+            s0, s1, m->row_begin, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p,
+            (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, nullptr,
+            nullptr, xl, yc, ex.yq, ex.qscale);
+    return;
+  }
   if (y_lower && dot)
     CFS_LAUNCH_SELL(0, true, false, true, m->sell_col.p, y_lower, dot);
   else if (y_lower)
@@ -304,7 +326,7 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
           s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,               \
           m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,                  \
           (const T *)m->diagonal.p, xb, yb, YL, DOTP, m->vcode.p,              \
-          (const T *)m->vdict.p, m->ndict, 0, xl, yc)
+          (const T *)m->vdict.p, m->ndict, 0, xl, yc, nullptr, nullptr)
 #define CFS_LAUNCH_BULK(HALO, DOT, YL, DOTP)                                   \
   do {                                                                         \
     auto kernel = reg::sym_spmv_reg_kernel<T, HALO, DOT, 0, false, true>;      \
@@ -319,7 +341,7 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
         s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p, m->vrow_row.p,  \
         m->ccol.p, (const T *)m->sell_val.p, (const T *)m->diagonal.p, xb, yb, \
         YL, DOTP, m->vcode.p, (const T *)m->vdict.p, m->ndict,                 \
-        m->max_slice_steps, xl, yc);                                           \
+        m->max_slice_steps, xl, yc, nullptr, nullptr);                         \
   } while (0)
 #define CFS_LAUNCH_REG_VI(HALO, DOT, SMEM, YL, DOTP)                           \
   do {                                                                         \
@@ -333,12 +355,29 @@ int launch_reg(const cfs_matrix_s *m, const T *xb, T *yb, T *y_lower,
               s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,           \
               m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,              \
               (const T *)m->diagonal.p, xb, yb, YL, DOTP, m->vcode.p,          \
-              (const T *)m->vdict.p, m->ndict, 0, xl, yc);                     \
+              (const T *)m->vdict.p, m->ndict, 0, xl, yc, nullptr, nullptr);   \
     else if (g_options.l2_prefetch)                                            \
       CFS_LAUNCH_REG(HALO, DOT, 0, true, SMEM, YL, DOTP);                      \
     else                                                                       \
       CFS_LAUNCH_REG(HALO, DOT, 0, false, SMEM, YL, DOTP);                     \
   } while (0)
+  if (ex.yq) { // deterministic mode (no halo fusion, no x'Ax: the caller checks)
+#define CFS_LAUNCH_DET(VI)                                                     \
+  reg::sym_spmv_reg_kernel<T, false, false, VI, false, false, 16, true>        \
+      <<<grid, reg::kThreads, 0, s>>>(                                         \
+          s0, s1, m->row_begin, m->slice_ptr.p, m->slice_cptr.p,               \
+          m->vrow_row.p, m->ccol.p, (const T *)m->sell_val.p,                  \
+          (const T *)m->diagonal.p, xb, yb, nullptr, nullptr, m->vcode.p,      \
+          (const T *)m->vdict.p, m->ndict, 0, xl, yc, ex.yq, ex.qscale)
+    if (vi == 2)
+      CFS_LAUNCH_DET(2);
+    else if (vi == 1)
+      CFS_LAUNCH_DET(1);
+    else
+      CFS_LAUNCH_DET(0);
+#undef CFS_LAUNCH_DET
+    return CFS_OK;
+  }
   // variant 7: value blocks staged by the TMA engine (streamed values only)
   const int bulk_smem =
       128 + (reg::kThreads / 32) * m->max_slice_steps * kSliceRows * (int)sizeof(T);
@@ -440,6 +479,18 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   // bounded column windows (banded / FEM orderings): products transposed
   // through shared memory, one coalesced RED per column and tile
   // (slice ranges of the host-vector pipeline: whole tiles only)
+  if (ex.yq) { // deterministic mode: the register kernels with integer REDs
+    ex.yq -= m->halo_begin;
+    if (m->ccol.p && m->nregular * 8 >= m->nslices)
+      return launch_reg<T>(m, xb, yb, nullptr, s, s0, s1, ex, nullptr);
+    if (!m->sell_col.p && m->padded_entries) {
+      set_error("deterministic mode needs the uncompressed column stream here: "
+                "set option keep_layouts=1 before cfs_cuda_matrix_tune");
+      return CFS_ERR_STATE;
+    }
+    launch_sell<T, 0>(m, xb, yb, nullptr, s, s0, s1, ex, nullptr);
+    return CFS_OK;
+  }
   if ((variant == 5 || variant == 6) && m->nt6 > 0 && g_options.tile6 &&
       mode == 0 && s0 % kT6Slices == 0 &&
       (s1 % kT6Slices == 0 || s1 == m->nslices))
@@ -512,6 +563,22 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   Extras ex;
   ex.x_lower = x_lower_base;
   ex.y_clear = y_clear;
+  // deterministic mode (det.cu): whole-matrix launches on one GPU
+  const bool det = g_options.deterministic && !y_lower_base && !xdoty &&
+                   slice0 == 0 && (slice1 < 0 || slice1 == m->nslices) &&
+                   m->nslices > 0;
+  if (g_options.deterministic && !det && m->nslices > 0) {
+    set_error("deterministic mode covers cfs_cuda_spmv / cfs_cuda_spmv_async on "
+              "one GPU (no fused halo, no x'Ax, no host-vector pipeline: set "
+              "option pipeline=0)");
+    return CFS_ERR_STATE;
+  }
+  if (det) {
+    CFS_TRY(det_prepare(m, x_ext, s));
+    ex.yq = m->det_acc.p;
+    ex.qscale = m->det_scale.p;
+    y_is_zero = true; // every row of y is written by det_finish
+  }
   if (slice1 < 0)
     slice1 = m->nslices;
   const size_t vs = m->vsize();
@@ -528,6 +595,8 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
               : launch_sym_typed<float>(m, y_ext, x_ext, y_lower_base, s,
                                         slice0, slice1, xdoty, ex));
   CFS_CUDA_TRY(cudaGetLastError());
+  if (det)
+    CFS_TRY(det_finish(m, y_ext, s));
   if (ev1)
     CFS_CUDA_TRY(cudaEventRecord(ev1, s));
   return CFS_OK;

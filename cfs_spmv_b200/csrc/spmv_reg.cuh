@@ -108,7 +108,7 @@ __device__ __forceinline__ void split_add(float &S, float &E, bool upper,
 // block is in flight. bulk_steps = the widest slice of the matrix (the stride
 // of a warp's piece). Copies of different warps overlap (tools/tma_bench.cu).
 template <typename T, bool HALO, bool DOT = false, int VI = 0, bool PF = false,
-          bool BULK = false, int MINB = 16>
+          bool BULK = false, int MINB = 16, bool DET = false>
 __global__ void __launch_bounds__(kThreads, MINB)
     sym_spmv_reg_kernel(long long slice_begin, long long slice_end,
                         int row_begin,
@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(kThreads, MINB)
                         const unsigned char *__restrict__ vcode,
                         const T *__restrict__ vdict, int ndict,
                         int bulk_steps, const T *__restrict__ x_lower,
-                        T *__restrict__ y_clear) {
+                        T *__restrict__ y_clear, long long *__restrict__ yq,
+                        const double *__restrict__ qscale) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ T sdict[VI == 1 ? kMaxDict : 1];
   T one_value = T(0);
@@ -139,6 +140,15 @@ __global__ void __launch_bounds__(kThreads, MINB)
       slice_begin + ((blockIdx.x * (long long)kThreads + threadIdx.x) >> 5);
   if (s >= slice_end)
     return;
+  // where a contribution to y[col] goes: an L2 reduction (of the GPU below for
+  // halo columns), or in deterministic mode an integer reduction into yq
+  const double scale = DET ? *qscale : 0.0;
+  auto emit = [&](int col, T v) {
+    if (DET)
+      tma::det_add(yq + col, (double)v, scale);
+    else
+      tma::y_add<HALO>(y, y_lower, row_begin, col, v);
+  };
   const int p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
   const T *sval = nullptr; // BULK: this warp's value block in shared memory
   uint64_t *bar = nullptr;
@@ -251,10 +261,10 @@ __global__ void __launch_bounds__(kThreads, MINB)
         acc += a0 * xv(0);
         S = a0 * xr;
       }
-      if (halo) { // chain reaches the rows of the GPU below
-        tma::y_add<true>(y, y_lower, row_begin, cbase + lane, S);
+      if (halo || DET) { // chain reaches the rows of the GPU below
+        emit(cbase + lane, S);
         if (lane < L - 1)
-          tma::y_add<true>(y, y_lower, row_begin, cbase + kSliceRows + lane, E);
+          emit(cbase + kSliceRows + lane, E);
       } else {
         T *yp = y + cbase + lane;
         tma::red_add(yp, S);
@@ -286,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
       for (int u = 0; u < kUnroll; ++u) {
         if (c[u] >= 0) {
           acc += a[u] * xc[u];
-          tma::y_add<HALO>(y, y_lower, row_begin, c[u], a[u] * xr);
+          emit(c[u], a[u] * xr);
         }
       }
       cp += kUnroll * kSliceRows;
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
       const T a = value_at(0);
       if (c >= 0) {
         acc += a * tma::x_at<HALO>(x, x_lower, row_begin, c);
-        tma::y_add<HALO>(y, y_lower, row_begin, c, a * xr);
+        emit(c, a * xr);
       }
       cp += kSliceRows;
       vp += kSliceRows;
@@ -310,7 +320,10 @@ __global__ void __launch_bounds__(kThreads, MINB)
     }
   }
   if (active) {
-    tma::red_add(y + row, acc);
+    if (DET)
+      tma::det_add(yq + row, (double)acc, scale);
+    else
+      tma::red_add(y + row, acc);
     // ping-pong result vectors: the row's owner clears the OTHER vector for the
     // next SpMV, which then needs no separate y initialisation
     if (y_clear && !(tag & kVrowCont))

@@ -89,6 +89,17 @@ __device__ __forceinline__ void y_add(T *y, T *y_lower, int row_begin, int col,
     red_add(y + col, v);
 }
 
+// Deterministic mode: a contribution is rounded ONCE to a multiple of
+// 1 / *scale (a power of two chosen from |A|, |x| and the longest row so that
+// no partial sum can overflow 63 bits) and added with an INTEGER reduction.
+// Integer addition is associative, so the value of q[col] does not depend on
+// the order in which the warps of the grid arrive -- y is bitwise reproducible
+// from run to run, which the order of floating-point REDs is not.
+__device__ __forceinline__ void det_add(long long *q, double v, double scale) {
+  const long long fixed = __double2ll_rn(v * scale);
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(q), "l"(fixed) : "memory");
+}
+
 // x[col]. With HALO the columns below row_begin are rows of the GPU below: they
 // are read straight from ITS x over NVLink (x_lower is that vector's virtual
 // base pointer; a caller that has pulled the halo into its own vector passes
