@@ -66,6 +66,8 @@ const char *cfs_cuda_version(void);
  *   "l2_prefetch"    0/1  variant 5 with streamed values: one L2 prefetch per
  *                    128-byte line of the slice's value block up front
  *   "reg_blocks"     16/12  resident 128-thread CTAs per SM variant 5 asks for
+ *   "deterministic"  0/1  y bitwise reproducible from run to run (integer
+ *                    reductions of contributions rounded once; see det.cu)
  *   "keep_layouts"   0/1  (tune time) keep the layouts of the kernel variants
  *                    that are not selected and the P = 1 lower CSR; default:
  *                    only for matrices below 4 M entries. Needed to switch

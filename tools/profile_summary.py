@@ -4,8 +4,10 @@ profiles/:  <tag>_launches.csv (verbatim launch list), <tag>_launch_shares.txt,
 <tag>_<kernel>_hot_sass.txt (stall samples per SASS line) and traffic.json
 (DRAM bytes per launch, read by bench.py).
 
-usage: python tools/profile_summary.py <tag> <launches.csv> <prof.ncu-rep> <kernel-short-name> [traffic-file]
-(traffic-file defaults to traffic.json, the one bench.py reads for the headline kernel)
+usage: python tools/profile_summary.py <tag> <launches.csv> <prof.ncu-rep> <kernel-short-name> <traffic-key>
+(traffic-key: the bench.py workload key under which the DRAM bytes per SpMV go
+into profiles/traffic.json, e.g. lap27_distinct_f64; a step that runs two
+kernels -- R-MAT: row kernel + hub kernel -- is the sum of both)
 """
 import collections
 import csv
@@ -51,7 +53,7 @@ def launches(tag, path):
                 n, t, 100 * t / tot, t / n, k[:110]))
 
 
-def details(tag, rep, kname, traffic_name="traffic.json"):
+def details(tag, rep, kname, traffic_key):
     rows = list(csv.reader(io.StringIO(ncu_page(rep, "details"))))
     h = rows[0]
     keep = [r for r in rows[1:] if r[h.index("ID")] == "0"]
@@ -66,28 +68,38 @@ def details(tag, rep, kname, traffic_name="traffic.json"):
 
     def metric(name, row):
         return float(row[hdr.index(name)].replace(",", ""))
-    per = []
+    per = collections.OrderedDict()  # kernel name -> launches
     for row in raw[2:]:
         units = raw[1]
         def in_bytes(name):
             v = metric(name, row)
             u = units[hdr.index(name)]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-        per.append({
+        per.setdefault(row[hdr.index("Kernel Name")][:80], []).append({
             "dram_bytes_read": in_bytes("dram__bytes_read.sum"),
             "dram_bytes_write": in_bytes("dram__bytes_write.sum"),
             "duration_us": metric("gpu__time_duration.sum", row) *
             {"us": 1, "ms": 1e3, "ns": 1e-3}[units[hdr.index("gpu__time_duration.sum")]],
         })
     t = {
-        "kernel": raw[2][hdr.index("Kernel Name")][:80],
-        "launches_captured": len(per),
-        "dram_bytes_per_launch": sum(p["dram_bytes_read"] + p["dram_bytes_write"]
-                                     for p in per) / len(per),
-        "per_launch": per,
+        "kernel": " + ".join(per.keys()),
+        "launches_captured": sum(len(v) for v in per.values()),
+        "dram_bytes_per_launch": sum(
+            sum(p["dram_bytes_read"] + p["dram_bytes_write"] for p in v) / len(v)
+            for v in per.values()),
+        "kernel_us": {k: sum(p["duration_us"] for p in v) / len(v)
+                      for k, v in per.items()},
+        "per_launch": [dict(p, kernel=k) for k, v in per.items() for p in v],
         "source": "ncu --set full --clock-control none, %s" % os.path.basename(rep),
+        "round": tag.split("_")[0],
     }
-    json.dump(t, open(os.path.join(OUT, traffic_name), "w"), indent=1)
+    tpath = os.path.join(OUT, "traffic.json")
+    try:
+        allt = json.load(open(tpath))
+    except Exception:
+        allt = {}
+    allt[traffic_key] = t
+    json.dump(allt, open(tpath, "w"), indent=1)
     # gather / atomic counters of the first captured launch (north star: L2 hit
     # rate of the x gathers, atomic / replay counters)
     wanted = [
@@ -156,10 +168,10 @@ def details(tag, rep, kname, traffic_name="traffic.json"):
 
 
 if __name__ == "__main__":
-    tag, lpath, rep, kname = sys.argv[1:5]
-    traffic_name = sys.argv[5] if len(sys.argv) > 5 else "traffic.json"
+    tag, lpath, rep, kname, traffic_key = sys.argv[1:6]
     os.makedirs(OUT, exist_ok=True)
     launches(tag, lpath)
-    details(tag, rep, kname, traffic_name)
+    details(tag, rep, kname, traffic_key)
     print(open(os.path.join(OUT, tag + "_launch_shares.txt")).read()[:1500])
-    print(open(os.path.join(OUT, traffic_name)).read()[:600])
+    t = json.load(open(os.path.join(OUT, "traffic.json")))[traffic_key]
+    print(traffic_key, t["dram_bytes_per_launch"], t["kernel_us"])
