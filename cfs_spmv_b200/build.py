@@ -25,7 +25,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 CUDA_SOURCES = ["cfs_cuda.cu", "preproc.cu", "windows.cu", "compress.cu", "tiles6.cu", "valindex.cu", "hubs.cu",
-                "refmeta.cu", "mmf_ingest.cu", "cg.cu", "csr_path.cu", "multi.cu", "det.cu",
+                "refmeta.cu", "mmf_ingest.cu", "cg.cu", "csr_path.cu", "multi.cu", "det.cu", "hyb.cu",
                 "spmv.cu", "gen.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

@@ -35,6 +35,7 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_matrix_create", "cfs_cuda_matrix_create_shard",
     "cfs_cuda_matrix_create_from_mmf", "cfs_cuda_matrix_download_csr",
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
+    "cfs_cuda_matrix_set_hybrid",
     "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_halo_async",
     "cfs_cuda_spmv_shard_async",
     "cfs_cuda_spmv_timed", "cfs_cuda_cg_solve",
@@ -104,7 +105,8 @@ class MatrixInfo(ctypes.Structure):
                 ("sort_window", ctypes.c_int64),
                 ("transposed_tiles", ctypes.c_int64),
                 ("tile_smem_bytes", ctypes.c_int64),
-                ("value_dictionary", ctypes.c_int64)]
+                ("value_dictionary", ctypes.c_int64),
+                ("hyb_far_entries", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -202,6 +204,7 @@ def lib():
     L.cfs_cuda_matrix_create_shard.argtypes = [ctypes.POINTER(vp), i32, i32,
                                                i32, vp, vp, vp, ctypes.c_int]
     L.cfs_cuda_matrix_tune.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    L.cfs_cuda_matrix_set_hybrid.argtypes = [vp, i32]
     L.cfs_cuda_matrix_create_from_mmf.argtypes = [
         ctypes.POINTER(vp), ctypes.POINTER(MmfText), ctypes.c_int,
         ctypes.c_int, ctypes.POINTER(MmfReport)]
@@ -338,6 +341,11 @@ class Matrix:
         check(lib().cfs_cuda_matrix_download_csr(self._h, _ptr(rp), _ptr(ci),
                                                  _ptr(v)))
         return rp, ci, v
+
+    def set_hybrid(self, threshold=10000):
+        """Format::hyb: entries at least `threshold` off the diagonal go to a
+        non-symmetric far part (call before tune)"""
+        check(lib().cfs_cuda_matrix_set_hybrid(self._h, threshold))
 
     def tune(self, nparts=1, tuning=1, allow_too_large=False):
         code = lib().cfs_cuda_matrix_tune(self._h, nparts, tuning)

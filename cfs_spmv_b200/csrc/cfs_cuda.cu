@@ -517,6 +517,22 @@ int cfs_cuda_matrix_create_shard(cfs_mat_t *out, int32_t global_nrows,
                        1);
 }
 
+int cfs_cuda_matrix_set_hybrid(cfs_mat_t m, int32_t bandwidth_threshold) {
+  if (!m || bandwidth_threshold < 0)
+    return CFS_ERR_INVALID;
+  if (m->tuned) {
+    set_error("cfs_cuda_matrix_set_hybrid: call it before cfs_cuda_matrix_tune");
+    return CFS_ERR_STATE;
+  }
+  if (!m->symmetric || m->sharded) {
+    set_error("cfs_cuda_matrix_set_hybrid: an unsharded symmetric matrix only "
+              "(csr_matrix.tpp:13-15: a general file quietly gives plain CSR)");
+    return CFS_ERR_INVALID;
+  }
+  m->hyb_threshold = bandwidth_threshold;
+  return CFS_OK;
+}
+
 int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
   // Tuning only selects the partitioner of a NON-symmetric matrix (:250-254)
   if (!m)
@@ -600,6 +616,10 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
       fprintf(stderr, "[tune] %-22s %8.2f ms\n", what, t1 - t0);
       t0 = t1;
     };
+    if (m->hyb_threshold > 0) { // Format::hyb: near part here, far part aside
+      CFS_TRY(split_hybrid(m, m->stream));
+      lap("hybrid split");
+    }
     CFS_TRY(build_lower(m, m->stream));
     lap("lower triangle");
     CFS_TRY(build_layout(m, m->stream));
@@ -679,6 +699,8 @@ void cfs_cuda_matrix_destroy(cfs_mat_t m) {
     cudaStreamDestroy(m->d2h_stream);
   if (m->stream)
     cudaStreamDestroy(m->stream);
+  if (m->far)
+    cfs_cuda_matrix_destroy(m->far);
   delete m;
 }
 
@@ -710,6 +732,7 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
   info->regular_slices = m->nregular;
   info->hub_columns = m->nhubs;
   info->hub_entries = m->hub_entries;
+  info->hyb_far_entries = m->far ? m->hyb_far_entries : 0;
   info->sort_window = m->sort_window;
   info->index_rows = m->ccol_rows;
   info->value_dictionary = m->ndict;
@@ -724,11 +747,16 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
       s += ((int64_t)m->ncolors + 1) * 4;
       s += 2LL * m->nranges * 4;
     }
+    if (m->far) // size(), csr_matrix.tpp:211-216: colind_high + values_high
+      s += m->hyb_far_entries * (4 + vs);
     info->size_bytes = s;
     // SURVEY.md 8(d)
     info->algorithmic_bytes = m->nnz_low * (vs + 4) + (int64_t)m->nrows * vs +
                               ((int64_t)m->nrows + 1) * 4 +
                               2 * (int64_t)m->nrows * vs;
+    if (m->far) // + the far part's CSR
+      info->algorithmic_bytes +=
+          m->hyb_far_entries * (vs + 4) + ((int64_t)m->nrows + 1) * 4;
   } else {
     info->size_bytes = ((int64_t)m->nrows + 1) * 4 + m->nnz_full * (4 + vs);
     if (m->part_by_nnz)
@@ -751,6 +779,11 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
                 m->range_ptr.bytes() + m->part_nranges.bytes() +
                 m->range_start.bytes() + m->range_end.bytes() +
                 m->stage_x.bytes() + m->stage_y.bytes());
+  if (m->far) {
+    cfs_matrix_info fi;
+    cfs_cuda_matrix_info(m->far, &fi);
+    info->device_bytes += fi.device_bytes;
+  }
   return CFS_OK;
 }
 

@@ -160,6 +160,11 @@ struct cfs_matrix_s {
 
   // execution layout: sliced ELL over virtual rows
   int64_t nvrows = 0, nslices = 0, padded_entries = 0;
+  // Format::hyb (hyb.cu): entries with |col - row| >= hyb_threshold live in
+  // `far`, a non-symmetric matrix whose kernel adds onto y after this one's
+  int hyb_threshold = 0;
+  int64_t hyb_far_entries = 0;
+  cfs_matrix_s *far = nullptr;
   int max_slice_steps = 0; // widest slice (steps of 32 entries)
   int max_row_nnz_full = 0; // longest row of the FULL matrix (terms one y gets)
   // deterministic mode (det.cu): 64-bit fixed-point y, {|A|max bits, |x|max
@@ -252,8 +257,11 @@ int build_layout_from(cfs_matrix_s *m, const int32_t *src_rowptr,
                       bool rechunk = false);
 // the non-symmetric path, Format::csr (csr_path.cu)
 int tune_csr(cfs_matrix_s *m, int nparts, int tuning, cudaStream_t s);
+// accumulate: add onto y instead of overwriting it (the far part of Format::hyb)
 int launch_csr_sell(const cfs_matrix_s *m, void *y, const void *x,
-                    cudaStream_t s);
+                    cudaStream_t s, bool accumulate = false);
+// Format::hyb (hyb.cu)
+int split_hybrid(cfs_matrix_s *m, cudaStream_t s);
 // x / y windows of the tiles (windows.cu)
 int build_windows(cfs_matrix_s *m, cudaStream_t s);
 // index-stream compression of regular slices (compress.cu)

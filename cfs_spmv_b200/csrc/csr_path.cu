@@ -178,8 +178,9 @@ int tune_csr(cfs_matrix_s *m, int nparts, int tuning, cudaStream_t s) {
 
 // declared in common.cuh next to the warp-per-row comparator kernel (spmv.cu)
 int launch_csr_sell(const cfs_matrix_s *m, void *y, const void *x,
-                    cudaStream_t s) {
-  CFS_CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)m->nrows * m->vsize(), s));
+                    cudaStream_t s, bool accumulate) {
+  if (!accumulate)
+    CFS_CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)m->nrows * m->vsize(), s));
   if (m->nslices == 0)
     return CFS_OK;
   const unsigned grid =

@@ -575,7 +575,7 @@ __global__ void slice_reach_kernel(long long nslices,
 // direction (tools/e2e_probe.py).
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
   m->stages.clear();
-  if (m->sharded || m->nslices < 4096)
+  if (m->sharded || m->far || m->nslices < 4096)
     return CFS_OK;
   // stage boundaries must not cut a sort window
   const long long unit =

@@ -564,6 +564,12 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   ex.x_lower = x_lower_base;
   ex.y_clear = y_clear;
   // deterministic mode (det.cu): whole-matrix launches on one GPU
+  const bool whole = slice0 == 0 && (slice1 < 0 || slice1 == m->nslices);
+  if (m->far && (!whole || y_lower_base || xdoty || g_options.deterministic)) {
+    set_error("a Format::hyb matrix runs whole, on one GPU, without x'Ax and "
+              "not in deterministic mode (its far part is a second kernel)");
+    return CFS_ERR_STATE;
+  }
   const bool det = g_options.deterministic && !y_lower_base && !xdoty &&
                    slice0 == 0 && (slice1 < 0 || slice1 == m->nslices) &&
                    m->nslices > 0;
@@ -585,8 +591,11 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   const size_t ext_len = (size_t)(m->row_begin + m->nrows - m->halo_begin);
   if (!y_is_zero)
     CFS_CUDA_TRY(cudaMemsetAsync(y_ext, 0, ext_len * vs, s));
-  if (m->nslices == 0 || slice1 <= slice0)
+  if (m->nslices == 0 || slice1 <= slice0) {
+    if (m->far)
+      CFS_TRY(launch_csr_sell(m->far, y_ext, x_ext, s, true));
     return CFS_OK;
+  }
   if (ev0)
     CFS_CUDA_TRY(cudaEventRecord(ev0, s));
   CFS_TRY(m->is_double
@@ -597,6 +606,8 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
   CFS_CUDA_TRY(cudaGetLastError());
   if (det)
     CFS_TRY(det_finish(m, y_ext, s));
+  if (m->far) // Format::hyb: the far part adds onto y (hyb.cu)
+    CFS_TRY(launch_csr_sell(m->far, y_ext, x_ext, s, true));
   if (ev1)
     CFS_CUDA_TRY(cudaEventRecord(ev1, s));
   return CFS_OK;

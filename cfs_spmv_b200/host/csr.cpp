@@ -161,8 +161,6 @@ CSRMatrix<IndexT, ValueT>::CSRMatrix(const string &filename, Platform platform,
       cout << "[INFO]: using " << (hybrid ? "HYB" : "SSS")
            << " format to store the sparse matrix..." << endl;
 #endif
-    if (nparts_ == 1)
-      hybrid_ = false;
     return;
   }
   MMF<IndexT, ValueT> mmf(filename);
@@ -202,8 +200,6 @@ CSRMatrix<IndexT, ValueT>::CSRMatrix(const string &filename, Platform platform,
   assert(filled == nnz_);
   for (IndexT i = 0; i < nrows_; ++i)
     rowptr_[i + 1] += rowptr_[i];
-  if (nparts_ == 1)
-    hybrid_ = false;
 }
 
 template <typename IndexT, typename ValueT>
@@ -215,10 +211,7 @@ CSRMatrix<IndexT, ValueT>::CSRMatrix(IndexT *rowptr, IndexT *colind,
       symmetric_(symmetric), hybrid_(hybrid), owns_data_(false), tuned_(false),
       nparts_((int)get_num_threads()), rowptr_(rowptr), colind_(colind),
       values_(values), device_(nullptr), multi_(nullptr),
-      ngpus_(get_num_gpus()), host_csr_pending_(false) {
-  if (nparts_ == 1)
-    hybrid_ = false;
-}
+      ngpus_(get_num_gpus()), host_csr_pending_(false) {}
 
 template <typename IndexT, typename ValueT>
 void CSRMatrix<IndexT, ValueT>::release_host_csr() {
@@ -302,7 +295,11 @@ bool CSRMatrix<IndexT, ValueT>::tune(Kernel, Tuning t) {
                                            is_double, symmetric_ ? 1 : 0),
                     "cfs_cuda_matrix_create");
   // Format::hyb: the reference's HYB split aborts for P > 1 and
-  // is switched off for P == 1; here it always runs as SSS.
+  // is switched off for P == 1 (csr_matrix.tpp:110, :143); here it runs for
+  // every P: the band inside HybBwThreshold symmetrically, the rest gathered
+  if (symmetric_ && hybrid_)
+    fatal_unless_ok(cfs_cuda_matrix_set_hybrid(device_, HybBwThreshold),
+                    "cfs_cuda_matrix_set_hybrid");
   int status = cfs_cuda_matrix_tune(
       device_, nparts_,
       t == Tuning::Aggressive ? CFS_TUNING_AGGRESSIVE : CFS_TUNING_NONE);

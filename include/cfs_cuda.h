@@ -196,6 +196,16 @@ int cfs_cuda_matrix_create_shard(cfs_mat_t *out, int32_t global_nrows,
  * reference is infeasible for this input (the SpMV path is still usable). */
 int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning);
 
+/* ---- Format::hyb: replaces split_by_bandwidth (csr_matrix.tpp:314-401) and the
+ * HYB kernels (:3031-3162), which the reference cannot reach (its tune() aborts
+ * for P > 1 and switches HYB off for P = 1). Call between create
+ * and tune on a symmetric matrix: entries with |col - row| >= threshold
+ * (HybBwThreshold = 10000, csr_matrix.hpp:92) are kept in BOTH triangles and
+ * only gathered (the Format::csr kernel adds them onto y); the band inside the
+ * threshold runs through the whole symmetric pipeline. nnz(), size() follow the
+ * reference's formulas; metadata export describes the near part. */
+int cfs_cuda_matrix_set_hybrid(cfs_mat_t m, int32_t bandwidth_threshold);
+
 void cfs_cuda_matrix_destroy(cfs_mat_t m); /* ~CSRMatrix, csr_matrix.tpp:147 */
 
 typedef struct cfs_matrix_info {
@@ -224,6 +234,8 @@ typedef struct cfs_matrix_info {
   int64_t tile_smem_bytes;  /* shared memory of the largest such tile         */
   int64_t value_dictionary; /* distinct values of the lower triangle when the
                                value stream is dictionary-coded (<= 256), else 0 */
+  int64_t hyb_far_entries;  /* Format::hyb: entries (both triangles) kept in the
+                               non-symmetric far part; 0 = none / not hybrid     */
 } cfs_matrix_info;
 
 int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info);

@@ -83,6 +83,10 @@ public:
   // device-side caller (a solver loop) use cfs_cuda_spmv_async directly.
   cfs_matrix_s *device_handle() const { return device_; }
 
+  // Format::hyb: entries at least this far from the diagonal go to the
+  // non-symmetric part (reference csr_matrix.hpp:92)
+  static constexpr int HybBwThreshold = 10000;
+
 private:
   Platform platform_;
   int nrows_, ncols_, nnz_;
