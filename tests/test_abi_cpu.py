@@ -141,3 +141,73 @@ def test_host_alloc_is_64_byte_aligned_and_freeable():
         ctypes.memset(p, 0xAB, nbytes)
         L.cfs_cuda_host_free(p)
     L.cfs_cuda_host_free(None)
+
+
+@pytest.mark.parametrize("points", [7, 27])
+def test_per_edge_coefficient_stencil_is_symmetric_and_dominant(points):
+    """seed != 0 (cfs_gen.h): one coefficient per edge -- the general-values
+    matrix bench.py measures by default"""
+    spec = capi.GenSpec.laplacian(points, 6, 5, 4, 7)
+    rp, ci, v = capi.gen_host_csr(spec)
+    n = len(rp) - 1
+    import scipy.sparse as sp
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    assert abs(A - A.T).max() == 0.0
+    off = A - sp.diags(A.diagonal())
+    assert np.all(off.data < -0.499) and np.all(off.data >= -1.0)
+    rowabs = np.asarray(abs(off).sum(axis=1)).ravel()
+    assert np.allclose(A.diagonal(), 0.0625 + rowabs, rtol=1e-15, atol=0)
+    assert len(np.unique(off.data)) == off.nnz // 2     # nothing to dictionary-code
+    # same pattern as the constant-coefficient stencil
+    rp0, ci0, _ = capi.gen_host_csr(capi.GenSpec.laplacian(points, 6, 5, 4))
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+    assert spec.ref_tool_spec().endswith(":7")
+
+
+def test_allocator_kinds_without_a_gpu():
+    """every kind degrades to plain 64-byte aligned memory on a host-only box"""
+    L = capi.lib()
+    for kind in (capi.CFS_ALLOC_DEFAULT, capi.CFS_ALLOC_PLAIN,
+                 capi.CFS_ALLOC_PINNED, capi.CFS_ALLOC_MANAGED):
+        p = L.cfs_cuda_host_alloc_kind(4096, kind)
+        assert p and p % 64 == 0
+        ctypes.memset(p, 0x5A, 4096)
+        assert L.cfs_cuda_vector_prefetch(p, 4096, 1) == 0   # optional, harmless
+        L.cfs_cuda_host_free(p)
+
+
+def test_new_entry_points_fail_loudly_without_a_gpu():
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    rp, ci, v = capi.gen_host_csr(capi.GenSpec.laplacian(7, 4, 4, 4))
+    with pytest.raises(capi.CfsError) as e:
+        capi.MultiMatrix(rp, ci, v, 2)
+    assert e.value.code == capi.CFS_ERR_NO_DEVICE
+    L = capi.lib()
+    assert L.cfs_cuda_matrix_set_hybrid(None, 100) == capi.CFS_ERR_INVALID
+    assert L.cfs_cuda_spmv_shard_async(None, None, None, None, None, None, 1,
+                                       None) == capi.CFS_ERR_INVALID
+    assert L.cfs_cuda_multi_spmv(None, None, None) == capi.CFS_ERR_INVALID
+    for key, val in (("deterministic", 1), ("deterministic", 0),
+                     ("keep_layouts", 0), ("l2_prefetch", 1),
+                     ("managed_prefetch", 1), ("spmv_variant", 7),
+                     ("spmv_variant", 5)):
+        capi.set_option(key, val)
+    with pytest.raises(capi.CfsError):
+        capi.set_option("deterministic", 2)
+
+
+def test_nnz_balanced_row_blocks():
+    """the split ShardedSpMV and cfs_cuda_multi_create use (partition_by_nnz
+    semantics lifted to GPUs): contiguous, aligned, about equal nnz"""
+    from cfs_spmv_b200.dist import nnz_balanced_blocks
+    rng = np.random.default_rng(0)
+    per_row = rng.integers(1, 60, size=10000)
+    per_row[:500] = 400                     # a heavy head
+    prefix = np.concatenate([[0], np.cumsum(per_row)])
+    for world in (2, 3, 8):
+        b = nnz_balanced_blocks(prefix, world)
+        assert b[0] == 0 and b[-1] == 10000 and len(b) == world + 1
+        assert all(x % 16 == 0 for x in b[:-1]) and b == sorted(b)
+        loads = [prefix[b[g + 1]] - prefix[b[g]] for g in range(world)]
+        assert max(loads) <= 1.1 * prefix[-1] / world + 400 * 16
