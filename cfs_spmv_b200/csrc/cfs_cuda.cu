@@ -638,6 +638,7 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
     lap("hub columns");
     CFS_TRY(build_pipeline_plan(m, m->stream));
     lap("pipeline plan");
+    CFS_TRY(build_halo_extent(m, m->stream));
     // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
     m->row_split.assign((size_t)nparts + 1, 0);
     if (nparts > 1) {

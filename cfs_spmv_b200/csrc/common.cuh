@@ -166,6 +166,7 @@ struct cfs_matrix_s {
   int64_t hyb_far_entries = 0;
   cfs_matrix_s *far = nullptr;
   int max_slice_steps = 0; // widest slice (steps of 32 entries)
+  long long halo_slice_end = 0; // shard: slices beyond never touch the halo
   int max_row_nnz_full = 0; // longest row of the FULL matrix (terms one y gets)
   // deterministic mode (det.cu): 64-bit fixed-point y, {|A|max bits, |x|max
   // bits} and {scale, 1/scale}; all built on first use
@@ -295,6 +296,7 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
 // deterministic mode (det.cu): before / after the kernel
 int det_prepare(const cfs_matrix_s *m, const void *x_ext, cudaStream_t s);
 int det_finish(const cfs_matrix_s *m, void *y_ext, cudaStream_t s);
+int build_halo_extent(cfs_matrix_s *m, cudaStream_t s);
 // host-vector pipeline plan (preproc.cu)
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,

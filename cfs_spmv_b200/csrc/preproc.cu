@@ -560,6 +560,46 @@ __global__ void slice_reach_kernel(long long nslices,
 }
 } // namespace
 
+namespace {
+__global__ void halo_extent_kernel(long long nslices, int row_begin,
+                                   const int *__restrict__ min_col,
+                                   int *__restrict__ out) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s < nslices && min_col[s] < row_begin)
+    atomicMax(out, (int)(s + 1));
+}
+} // namespace
+
+// A shard: one past the last slice that references a column below row_begin.
+// Only slices [0, halo_slice_end) need the kernel instantiations that test
+// every column against row_begin (x from / reductions into the GPU below); in
+// a banded or stencil shard that is the first 0.1 - 2 % of the slices.
+int build_halo_extent(cfs_matrix_s *m, cudaStream_t s) {
+  m->halo_slice_end = m->nslices;
+  if (!m->sharded || m->nslices == 0 || !m->sell_col.p)
+    return CFS_OK;
+  const long long ns = m->nslices;
+  DevArray<int> d_min, d_rlo, d_rhi, d_out;
+  CFS_TRY(d_min.alloc((size_t)ns));
+  CFS_TRY(d_rlo.alloc((size_t)ns));
+  CFS_TRY(d_rhi.alloc((size_t)ns));
+  CFS_TRY(d_out.alloc(1));
+  CFS_CUDA_TRY(cudaMemsetAsync(d_out.p, 0, 4, s));
+  slice_reach_kernel<<<blocks_for((size_t)ns * 32), kThreads, 0, s>>>(
+      ns, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p, d_min.p, d_rlo.p,
+      d_rhi.p);
+  halo_extent_kernel<<<blocks_for((size_t)ns), kThreads, 0, s>>>(
+      ns, m->row_begin, d_min.p, d_out.p);
+  CFS_CUDA_TRY(cudaGetLastError());
+  int end = 0;
+  CFS_CUDA_TRY(cudaMemcpyAsync(&end, d_out.p, 4, cudaMemcpyDeviceToHost, s));
+  CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  // whole tiles of variant 6 / whole CTAs of the others
+  m->halo_slice_end = std::min<long long>(
+      ns, ((long long)end + kT6Slices - 1) / kT6Slices * kT6Slices);
+  return CFS_OK;
+}
+
 // Stages of the host-vector pipeline of cfs_cuda_spmv (see cfs_matrix_s::Stage),
 // for an unsharded matrix whose slices follow the row order at least block-wise:
 // natural order, or rows length-sorted inside windows (stage boundaries then

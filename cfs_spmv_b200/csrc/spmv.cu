@@ -465,6 +465,17 @@ template <typename T>
 int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                      void *y_lower_base, cudaStream_t s, long long s0,
                      long long s1, double *dot, Extras ex) {
+  // A shard with a fused halo: only its first slices reach below row_begin, the
+  // rest runs the plain instantiation (no per-column test against row_begin)
+  if (y_lower_base && !dot && m->halo_slice_end < s1) {
+    const long long hs = m->halo_slice_end > s0 ? m->halo_slice_end : s0;
+    if (hs > s0)
+      CFS_TRY(launch_sym_typed<T>(m, y_ext, x_ext, y_lower_base, s, s0, hs, dot,
+                                  ex));
+    Extras rest = ex;
+    rest.x_lower = nullptr;
+    return launch_sym_typed<T>(m, y_ext, x_ext, nullptr, s, hs, s1, dot, rest);
+  }
   // the row owners index y_clear by global row id like y
   if (ex.y_clear)
     ex.y_clear = (T *)ex.y_clear - m->halo_begin;
