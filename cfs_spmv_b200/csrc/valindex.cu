@@ -163,6 +163,15 @@ template <typename T> int build_typed(cfs_matrix_s *m, cudaStream_t s) {
     CFS_CUDA_TRY(cudaMemcpy(&filler, val + at, sizeof(U),
                             cudaMemcpyDeviceToHost));
   }
+  // a matrix with per-entry values (any real FEM matrix) is recognised from
+  // 4096 strided entries: no code array, no large sort
+  {
+    std::vector<U> few;
+    const long long stride = n > 4096 ? n / 4096 : 1;
+    CFS_TRY(distinct_values<U>(val, col, n, stride, filler, few, s));
+    if (few.empty() || (int)few.size() > kMaxDict)
+      return CFS_OK;
+  }
   CFS_TRY(m->vcode.alloc((size_t)n));
   DevArray<U> dict;
   DevArray<int> missing;
