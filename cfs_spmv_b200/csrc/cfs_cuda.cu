@@ -636,8 +636,8 @@ int cfs_cuda_matrix_tune(cfs_mat_t m, int nparts, int tuning) {
     lap("value index");
     CFS_TRY(build_hubs(m, m->stream));
     lap("hub columns");
-    CFS_TRY(build_pipeline_plan(m, m->stream));
-    lap("pipeline plan");
+    CFS_TRY(build_pipeline_reach(m, m->stream));
+    lap("pipeline reach");
     CFS_TRY(build_halo_extent(m, m->stream));
     // row_split_ (partition_by_nrows, csr_matrix.tpp:418-423)
     m->row_split.assign((size_t)nparts + 1, 0);
@@ -779,7 +779,9 @@ int cfs_cuda_matrix_info(cfs_mat_t m, cfs_matrix_info *info) {
                 m->adj.bytes() + m->color.bytes() + m->color_first.bytes() +
                 m->range_ptr.bytes() + m->part_nranges.bytes() +
                 m->range_start.bytes() + m->range_end.bytes() +
-                m->stage_x.bytes() + m->stage_y.bytes());
+                m->stage_x.bytes() + m->stage_y.bytes() +
+                m->reach_min.bytes() + m->reach_rlo.bytes() +
+                m->reach_rhi.bytes());
   if (m->far) {
     cfs_matrix_info fi;
     cfs_cuda_matrix_info(m->far, &fi);
@@ -1011,6 +1013,9 @@ int cfs_cuda_spmv(cfs_mat_t m, void *y, const void *x) {
   bool px = false, py = false, mx = false, my = false;
   classify(x, &kx, &px, &mx);
   classify(y, &ky, &py, &my);
+  if (kx == kPtrHost && ky == kPtrHost && m->symmetric && m->plan_state == 1 &&
+      g_options.pipeline && !g_options.deterministic)
+    CFS_TRY(build_pipeline_plan(m, m->stream)); // first call with host vectors
   if (kx == kPtrHost && ky == kPtrHost && m->symmetric && !m->stages.empty() &&
       g_options.pipeline && !g_options.deterministic)
     return spmv_host_pipelined(m, y, x, px && py);

@@ -238,6 +238,9 @@ struct cfs_matrix_s {
     std::vector<std::pair<int, int>> y_ready;
   };
   std::vector<Stage> stages;
+  // 0: untuned, 1: per-slice reach on the device, plan pending, 2: plan final
+  int plan_state = 0;
+  cfsb::DevArray<int> reach_min, reach_rlo, reach_rhi;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> ev_x, ev_k, ev_d;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -297,7 +300,8 @@ int launch_sym_spmv(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
 int det_prepare(const cfs_matrix_s *m, const void *x_ext, cudaStream_t s);
 int det_finish(const cfs_matrix_s *m, void *y_ext, cudaStream_t s);
 int build_halo_extent(cfs_matrix_s *m, cudaStream_t s);
-// host-vector pipeline plan (preproc.cu)
+// host-vector pipeline plan (preproc.cu): tune-time half and first-use half
+int build_pipeline_reach(cfs_matrix_s *m, cudaStream_t s);
 int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s);
 int launch_csr_spmv(const cfs_matrix_s *m, void *y, const void *x,
                     cudaStream_t s);

@@ -613,8 +613,17 @@ int build_halo_extent(cfs_matrix_s *m, cudaStream_t s) {
 // rows of x) the D2H of chunk c-1 starts, while the H2D of the rest of chunk c
 // is still under way. Without the split y lags x by a whole chunk in each
 // direction (tools/e2e_probe.py).
-int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
+// Tune-time half: what the plan needs from the column stream (which may be
+// released after tune) -- per slice its smallest column and its row span, 12
+// bytes per slice, kept on the device. The plan itself is made by
+// build_pipeline_plan on the first call with host vectors: callers whose vectors
+// live in unified or device memory never pay for it (7 ms of tune on config 2).
+int build_pipeline_reach(cfs_matrix_s *m, cudaStream_t s) {
   m->stages.clear();
+  m->plan_state = 2; // nothing to plan
+  m->reach_min.release();
+  m->reach_rlo.release();
+  m->reach_rhi.release();
   if (m->sharded || m->far || m->nslices < 4096)
     return CFS_OK;
   // stage boundaries must not cut a sort window
@@ -623,23 +632,37 @@ int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
   if (m->sort_window % kSliceRows != 0 || unit * 64 > m->nslices)
     return CFS_OK; // globally sorted (power-law matrices): no row order left
   const long long ns = m->nslices;
-  DevArray<int> d_min, d_rlo, d_rhi;
-  CFS_TRY(d_min.alloc((size_t)ns));
-  CFS_TRY(d_rlo.alloc((size_t)ns));
-  CFS_TRY(d_rhi.alloc((size_t)ns));
+  CFS_TRY(m->reach_min.alloc((size_t)ns));
+  CFS_TRY(m->reach_rlo.alloc((size_t)ns));
+  CFS_TRY(m->reach_rhi.alloc((size_t)ns));
   slice_reach_kernel<<<blocks_for((size_t)ns * 32), kThreads, 0, s>>>(
-      ns, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p, d_min.p, d_rlo.p,
-      d_rhi.p);
+      ns, m->slice_ptr.p, m->vrow_row.p, m->sell_col.p, m->reach_min.p,
+      m->reach_rlo.p, m->reach_rhi.p);
   CFS_CUDA_TRY(cudaGetLastError());
+  m->plan_state = 1; // reach known, plan pending
+  return CFS_OK;
+}
+
+int build_pipeline_plan(cfs_matrix_s *m, cudaStream_t s) {
+  m->stages.clear();
+  if (m->plan_state != 1)
+    return CFS_OK;
+  m->plan_state = 2;
+  const long long unit =
+      m->sort_window == 0 ? 1 : m->sort_window / kSliceRows;
+  const long long ns = m->nslices;
   std::vector<int> min_col((size_t)ns), min_row((size_t)ns),
       max_row((size_t)ns);
-  CFS_CUDA_TRY(cudaMemcpyAsync(min_col.data(), d_min.p, (size_t)ns * 4,
+  CFS_CUDA_TRY(cudaMemcpyAsync(min_col.data(), m->reach_min.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
-  CFS_CUDA_TRY(cudaMemcpyAsync(min_row.data(), d_rlo.p, (size_t)ns * 4,
+  CFS_CUDA_TRY(cudaMemcpyAsync(min_row.data(), m->reach_rlo.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
-  CFS_CUDA_TRY(cudaMemcpyAsync(max_row.data(), d_rhi.p, (size_t)ns * 4,
+  CFS_CUDA_TRY(cudaMemcpyAsync(max_row.data(), m->reach_rhi.p, (size_t)ns * 4,
                                cudaMemcpyDeviceToHost, s));
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
+  m->reach_min.release();
+  m->reach_rlo.release();
+  m->reach_rhi.release();
   int K = g_options.pipeline_chunks;
   if (g_options.pipeline_adaptive) {
     // every stage costs 10-25 us of hand-overs: keep >= 4 MB of x per chunk

@@ -24,6 +24,7 @@ def _matrices():
     yield "lap7", capi.gen_host_csr(capi.GenSpec.laplacian(7, 33, 17, 60)), 1
     yield "banded", capi.gen_host_csr(capi.GenSpec.banded(60000, 700, 152, 3)), 1
     yield "rmat", gen.rmat(14, 8, 1), 0
+    yield "rmat_18", gen.rmat(18, 8, 1), 0
     yield "ragged", gen.random_symmetric(5000, 6, 11), 0
 
 
