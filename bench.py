@@ -593,14 +593,15 @@ def main():
             "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None,
             "dtype": "f64" if is_double else "f32", "data": "synthetic",
-            "config": dict(workload_config(args, world, nnz_full,
-                                           info["nrows"] if world == 1 else None),
-                           setup_s=round(setup_s, 2),
-                           exchange=exchange_desc,
-                           layout={k: info[k] for k in
+            # the same keys and values as the reference arm's line
+            "config": workload_config(args, world),
+            "details": {"nnz_full_counted": nnz_full,
+                        "setup_s": round(setup_s, 2),
+                        "exchange": exchange_desc,
+                        "layout": {k: info[k] for k in
                                    ("nnz_low", "nvrows", "nslices",
                                     "padded_entries", "device_bytes",
-                                    "value_dictionary")}),
+                                    "value_dictionary")}},
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

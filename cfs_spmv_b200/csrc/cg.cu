@@ -252,9 +252,19 @@ int solve(cfs_matrix_s *m, T *x, const T *b, int max_iters, double rel_tol,
   double *pq = (double *)((char *)st.p + offsetof(CgState, pq));
   const int grid = grid_for(n);
 
-  cudaEvent_t e0, e1;
-  CFS_CUDA_TRY(cudaEventCreate(&e0));
-  CFS_CUDA_TRY(cudaEventCreate(&e1));
+  // released on every way out, the early error returns included
+  struct Events {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() {
+      if (a)
+        cudaEventDestroy(a);
+      if (b)
+        cudaEventDestroy(b);
+    }
+  } events;
+  CFS_CUDA_TRY(cudaEventCreate(&events.a));
+  CFS_CUDA_TRY(cudaEventCreate(&events.b));
+  const cudaEvent_t e0 = events.a, e1 = events.b;
   CFS_CUDA_TRY(cudaEventRecord(e0, s));
 
   // r = b - A x0
@@ -271,6 +281,13 @@ int solve(cfs_matrix_s *m, T *x, const T *b, int max_iters, double rel_tol,
   // one iteration, captured once
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  // (in deterministic mode launch_sym_spmv refuses x'Ax: say so before a
+  // capture is open)
+  if (g_options.deterministic) {
+    set_error("cfs_cuda_cg_solve: not available in deterministic mode (its "
+              "SpMV also returns p'Ap)");
+    return CFS_ERR_STATE;
+  }
   CFS_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int status = launch_sym_spmv(m, q.p, p.p, s, nullptr, nullptr, nullptr, true,
                                0, -1, pq);
@@ -320,8 +337,6 @@ int solve(cfs_matrix_s *m, T *x, const T *b, int max_iters, double rel_tol,
   cudaEventSynchronize(e1);
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (exec)
     cudaGraphExecDestroy(exec);
   if (status != CFS_OK)
