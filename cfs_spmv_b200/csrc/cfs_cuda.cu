@@ -192,6 +192,10 @@ static int set_option_checked(const char *key, long long value) {
     g_options.csr_layout = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "slot_banks") && (value == 0 || value == 1)) {
+    g_options.slot_banks = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "deterministic") && (value == 0 || value == 1)) {
     g_options.deterministic = (int)value;
     return CFS_OK;

@@ -65,15 +65,22 @@ __global__ void __launch_bounds__(kBoundsThreads)
 }
 
 // per tile: histogram over the window -> slot offsets (cptr) -> a slot for
-// every entry. The order of the entries of one column is the order in which
-// their atomics land: fixed once here, the same for every later SpMV.
+// every entry. Which of its column's slots an entry gets is free, and it
+// decides the shared-memory bank the SpMV kernel's product store hits: ncu had
+// those stores at 6.3-way bank conflicts (10.6 M of 15.4 M wavefronts) when the
+// slots were handed out in the order the atomics landed. Here warp w walks the
+// steps of slice w exactly like the SpMV kernel will, and in every step its
+// lanes pick, one after the other, a free slot of their column whose bank no
+// earlier lane of the same store wavefront has taken (`banks` = 16 bank pairs
+// per half warp for 8-byte products, 32 banks per warp for 4-byte ones).
+// Columns with more than 32 entries in the tile keep the first-come order.
 __global__ void __launch_bounds__(kSlotThreads)
     tile_slots_kernel(long long nslices, const int *__restrict__ slice_ptr,
                       const int *__restrict__ sell_col,
                       const int *__restrict__ lo, const int *__restrict__ ncols,
                       const long long *__restrict__ cptr_off,
                       unsigned short *__restrict__ cptr,
-                      unsigned *__restrict__ pack) {
+                      unsigned *__restrict__ pack, int banks) {
   extern __shared__ int window[];
   int *start = window;               // histogram, then exclusive offsets
   int *cursor = window + kT6MaxCols;
@@ -114,15 +121,56 @@ __global__ void __launch_bounds__(kSlotThreads)
   // W < kT6MaxCols and the bins beyond the window are empty: start[W] = total
   for (int j = threadIdx.x; j <= W; j += kSlotThreads)
     out[j] = (unsigned short)start[j];
-  for (size_t e = begin + threadIdx.x; e < end; e += kSlotThreads) {
-    const int c = sell_col[e];
-    unsigned p = 0xffffffffu;
-    if (c >= 0) {
-      const int j = c - base;
-      const int slot = start[j] + atomicAdd(&cursor[j], 1);
-      p = (unsigned)j | ((unsigned)slot << 16);
+  __syncthreads();
+  // cursor[j]: bit mask of the used slots of column j (<= 32 entries), or the
+  // number of slots handed out (longer columns)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long sl = tile * kT6Slices + warp;
+  if (sl < nslices) {
+    const int p0 = slice_ptr[sl], width = slice_ptr[sl + 1] - p0;
+    const int group = banks == 16 ? lane >> 4 : 0; // store wavefront of the lane
+    for (int k = 0; k < width; ++k) {
+      const size_t e = ((size_t)p0 + k) * kSliceRows + lane;
+      const int c = sell_col[e];
+      const int j = c >= 0 ? c - base : 0;
+      const int first = c >= 0 ? start[j] : 0;
+      const int n = c >= 0 ? start[j + 1] - first : 0;
+      int slot = -1;
+      unsigned taken[2] = {0u, 0u}; // banks claimed per store wavefront
+      for (int turn = 0; turn < 32; ++turn) {
+        int bank = -1;
+        if (lane == turn && c >= 0) {
+          if (n > 32) {
+            slot = first + atomicAdd(&cursor[j], 1);
+          } else {
+            const unsigned all = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+            while (slot < 0) {
+              const unsigned free_bits = ~(unsigned)cursor[j] & all;
+              // first free slot on a bank nobody in this wavefront holds, else
+              // the first free one
+              int pick = -1;
+              for (unsigned f = free_bits; f; f &= f - 1) {
+                const int b = __ffs(f) - 1;
+                if (!((taken[group] >> ((first + b) & (banks - 1))) & 1u)) {
+                  pick = b;
+                  break;
+                }
+              }
+              if (pick < 0)
+                pick = __ffs(free_bits) - 1;
+              const unsigned bit = 1u << pick;
+              if (!((unsigned)atomicOr(&cursor[j], (int)bit) & bit))
+                slot = first + pick; // else another warp took it: look again
+            }
+          }
+          bank = slot & (banks - 1);
+        }
+        bank = __shfl_sync(0xffffffffu, bank, turn);
+        if (bank >= 0)
+          taken[banks == 16 ? turn >> 4 : 0] |= 1u << bank;
+      }
+      pack[e] = c >= 0 ? ((unsigned)j | ((unsigned)slot << 16)) : 0xffffffffu;
     }
-    pack[e] = p;
   }
 }
 
@@ -182,7 +230,8 @@ int build_tiles6(cfs_matrix_s *m, cudaStream_t s) {
                                     slot_smem));
   tile_slots_kernel<<<(unsigned)nt, kSlotThreads, slot_smem, s>>>(
       m->nslices, m->slice_ptr.p, m->sell_col.p, m->t6_lo.p, m->t6_ncols.p,
-      m->t6_cptr_off.p, m->t6_cptr.p, m->t6_pack.p);
+      m->t6_cptr_off.p, m->t6_cptr.p, m->t6_pack.p,
+      g_options.slot_banks ? (m->is_double ? 16 : 32) : 1);
   CFS_CUDA_TRY(cudaGetLastError());
   CFS_CUDA_TRY(cudaStreamSynchronize(s));
   m->nt6 = nt;
