@@ -327,8 +327,8 @@ def run_reference(args, rank, world):
     share = ""
     if args.gpus > 1 and args.scaling == "weak" and args.workload != "rmat":
         share = (" -- ONE GPU's share of the N=%d workload (the rate is "
-                 "size-independent to first order; the N-GPU matrix itself "
-                 "needs > 60 GB as the reference's host CSR)" % args.gpus)
+                 "size-independent to first order; as the reference's host CSR "
+                 "the whole matrix grows to > 60 GB at N = 8)" % args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": out["value"],
         "unit": UNIT, "n_gpus": args.gpus, "steps": loops,
