@@ -20,6 +20,7 @@
 //       to the touched ranges, read over peer access) -- "strips".
 #include <algorithm>
 #include <string.h>
+#include <time.h>
 
 #include "common.cuh"
 
@@ -37,6 +38,11 @@ struct cfs_multi_s {
   std::vector<cudaStream_t> stream;
   std::vector<cudaEvent_t> ready, done; // y cleared + x in / kernel finished
   std::vector<void *> x_ext, y_ext;     // device buffers over [halo_begin, row_end)
+  // unified-memory vectors the GPUs work on in place (zero_copy_spmv): the last
+  // pair that was advised and prefetched, and how long a call on it may take
+  const void *zc_x = nullptr;
+  void *zc_y = nullptr;
+  double zc_expect_us = 0;
   size_t vsize() const { return is_double ? 8 : 4; }
 };
 
@@ -234,7 +240,94 @@ int cfs_cuda_multi_tune(cfs_multi_t mm) {
     CFS_CUDA_TRY(cudaMalloc(&mm->x_ext[g], (len ? len : 1) * vs));
     CFS_CUDA_TRY(cudaMalloc(&mm->y_ext[g], (len ? len : 1) * vs));
   }
+  // generous bound for a fault-free call (cfs_cuda_spmv uses the same rule)
+  mm->zc_expect_us =
+      200.0 + 4.0 * (double)(mm->nnz_low * (vs + 4) + 4ll * mm->nrows * vs) / 3e6 / G;
   return cfs_cuda_init(mm->device[0]);
+}
+
+// x and y are unified memory (what internal_alloc hands the reference's bench
+// and test) and the halos are fused: the GPUs work on the caller's vectors IN
+// PLACE, no copy in, no copy out. x is advised read-mostly -- every GPU keeps a
+// local duplicate of the pages it reads, a host write collapses them -- and the
+// rows [R_g, R_g+1) of y prefer GPU g and are mapped into the GPU above, whose
+// kernel reduces its halo contributions into them over NVLink (the kernels
+// index both vectors by global ids already, so y itself is the "y of the GPU
+// below"). Per call: every GPU clears its rows, the kernels, one join.
+static double multi_wall_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+static int zero_copy_spmv(cfs_multi_t mm, void *y, const void *x) {
+  const int G = mm->ngpus;
+  const size_t vs = mm->vsize();
+  const double t0 = multi_wall_us();
+  bool moved = false;
+  if (mm->zc_x != x) {
+    CFS_CUDA_TRY(cudaMemAdvise(x, (size_t)mm->nrows * vs,
+                               cudaMemAdviseSetReadMostly, mm->device[0]));
+    for (int g = 0; g < G; ++g) {
+      const size_t len = (size_t)(mm->bound[g + 1] - mm->halo_begin[g]);
+      if (len)
+        CFS_CUDA_TRY(cudaMemPrefetchAsync(
+            (const char *)x + (size_t)mm->halo_begin[g] * vs, len * vs,
+            mm->device[g], mm->stream[g]));
+    }
+    mm->zc_x = x;
+    moved = true;
+  }
+  if (mm->zc_y != y) {
+    for (int g = 0; g < G; ++g) {
+      char *rows = (char *)y + (size_t)mm->bound[g] * vs;
+      const size_t bytes = (size_t)(mm->bound[g + 1] - mm->bound[g]) * vs;
+      if (!bytes)
+        continue;
+      CFS_CUDA_TRY(cudaMemAdvise(rows, bytes, cudaMemAdviseSetPreferredLocation,
+                                 mm->device[g]));
+      CFS_CUDA_TRY(cudaMemAdvise(rows, bytes, cudaMemAdviseSetAccessedBy,
+                                 mm->device[g]));
+      if (g + 1 < G) // the GPU above reduces into these rows
+        CFS_CUDA_TRY(cudaMemAdvise(rows, bytes, cudaMemAdviseSetAccessedBy,
+                                   mm->device[g + 1]));
+      CFS_CUDA_TRY(cudaMemPrefetchAsync(rows, bytes, mm->device[g],
+                                        mm->stream[g]));
+    }
+    mm->zc_y = y;
+    moved = true;
+  }
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    CFS_CUDA_TRY(cudaMemsetAsync((char *)y + (size_t)mm->bound[g] * vs, 0,
+                                 (size_t)(mm->bound[g + 1] - mm->bound[g]) * vs,
+                                 mm->stream[g]));
+    CFS_CUDA_TRY(cudaEventRecord(mm->ready[g], mm->stream[g]));
+  }
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    const bool halo = g > 0 && mm->halo_begin[g] < mm->bound[g];
+    if (halo)
+      CFS_CUDA_TRY(cudaStreamWaitEvent(mm->stream[g], mm->ready[g - 1], 0));
+    // extended vectors over [halo_begin, row_end) = the caller's vectors from
+    // halo_begin on; their virtual base is the caller's pointer itself
+    CFS_TRY(cfs_cuda_spmv_shard_async(
+        mm->shard[g], (char *)y + (size_t)mm->halo_begin[g] * vs,
+        (const char *)x + (size_t)mm->halo_begin[g] * vs, halo ? y : nullptr,
+        nullptr, nullptr, 1, mm->stream[g]));
+  }
+  for (int g = 0; g < G; ++g) {
+    CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+    CFS_CUDA_TRY(cudaStreamSynchronize(mm->stream[g]));
+  }
+  CFS_CUDA_TRY(cudaSetDevice(mm->device[0]));
+  // a call that took far longer than the matrix can explain met pages the host
+  // had touched (it read y, it rewrote x): advise and prefetch again next time
+  if (!moved && multi_wall_us() - t0 > mm->zc_expect_us) {
+    mm->zc_x = nullptr;
+    mm->zc_y = nullptr;
+  }
+  return CFS_OK;
 }
 
 int cfs_cuda_multi_spmv(cfs_multi_t mm, void *y, const void *x) {
@@ -246,6 +339,14 @@ int cfs_cuda_multi_spmv(cfs_multi_t mm, void *y, const void *x) {
   }
   const int G = mm->ngpus;
   const size_t vs = mm->vsize();
+  if (mm->fused && g_options.multi_zero_copy) {
+    cudaPointerAttributes ax, ay;
+    if (cudaPointerGetAttributes(&ax, x) == cudaSuccess &&
+        cudaPointerGetAttributes(&ay, y) == cudaSuccess &&
+        ax.type == cudaMemoryTypeManaged && ay.type == cudaMemoryTypeManaged)
+      return zero_copy_spmv(mm, y, x);
+    cudaGetLastError();
+  }
   // 1. every GPU: its piece of x in, its y clear
   for (int g = 0; g < G; ++g) {
     CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));

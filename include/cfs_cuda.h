@@ -297,8 +297,12 @@ int cfs_cuda_spmv_shard_async(cfs_mat_t m, void *y_dev, const void *x_dev,
  * NVLink peer access when every halo lies inside that one block (banded /
  * stencil matrices, fused_halo = 1), else the owners add the strips the GPUs
  * above produced for them (a reduce-scatter restricted to the touched ranges;
- * R-MAT). rowptr / colind / values: FULL CSR in host memory, borrowed during
- * the call only. */
+ * R-MAT). With fused halos and x, y in unified memory (cfs_cuda_host_alloc)
+ * the GPUs work on the caller's vectors in place: x advised read-mostly (local
+ * duplicates per GPU), the rows of y preferring their owner and mapped into the
+ * GPU above; nothing is copied (option multi_zero_copy, default 1).
+ * rowptr / colind / values: FULL CSR in host memory, borrowed during the call
+ * only. */
 typedef struct cfs_multi_s *cfs_multi_t;
 #define CFS_MULTI_MAX_GPUS 16
 typedef struct cfs_multi_info {

@@ -86,3 +86,42 @@ def test_reference_programs_on_several_gpus(gpu, ngpus, tmp_path):
         assert r.returncode == 0 and "gflops/s" in r.stdout, r.stdout + r.stderr
         r = _run("api_consumer", [path, "0"], env)
         assert r.returncode == 0 and "ALL PASSED!" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_unified_memory_vectors_are_used_in_place(gpu, ngpus):
+    """managed x / y (what internal_alloc hands out) + fused halos: the GPUs
+    read x and write y where they are; the host rewrites x and reads y between
+    calls"""
+    import ctypes
+    if gpu.device_count() < ngpus:
+        pytest.skip("needs %d GPUs" % ngpus)
+    L = capi.lib()
+    for name, spec in (("lap27", capi.GenSpec.laplacian(27, 48, 40, 64, 7)),
+                       ("banded", capi.GenSpec.banded(200000, 700, 152, 3))):
+        rp, ci, v = capi.gen_host_csr(spec)
+        n = len(rp) - 1
+        o = oracle.Oracle(rp, ci, v, 1)
+        A = capi.MultiMatrix(rp, ci, v, ngpus)
+        assert A.info()["fused_halo"] == 1
+        px = L.cfs_cuda_host_alloc_kind(n * 8, capi.CFS_ALLOC_MANAGED)
+        py = L.cfs_cuda_host_alloc_kind(n * 8, capi.CFS_ALLOC_MANAGED)
+        x = np.ctypeslib.as_array(ctypes.cast(px, ctypes.POINTER(ctypes.c_double)), (n,))
+        y = np.ctypeslib.as_array(ctypes.cast(py, ctypes.POINTER(ctypes.c_double)), (n,))
+        x[:] = gen.gen_x(2, n)
+        y[:] = 5.0
+        for rep in range(5):
+            A.spmv(py, px)
+            ref = o.spmv(np.array(x))
+            assert cases.normwise_rel_err(np.array(y), ref) <= 1e-12, (name, rep)
+            if rep % 2 == 0:        # the host rewrites x and scribbles over y
+                x *= 1.25
+                y[::5] = -1.0
+        for opt in (0, 1):          # the copying path gives the same
+            capi.set_option("multi_zero_copy", opt)
+            A.spmv(py, px)
+            assert cases.normwise_rel_err(np.array(y), o.spmv(np.array(x))) <= 1e-12
+        A.close()
+        L.cfs_cuda_host_free(px)
+        L.cfs_cuda_host_free(py)
+    capi.init(0)
