@@ -192,6 +192,10 @@ static int set_option_checked(const char *key, long long value) {
     g_options.csr_layout = (int)value;
     return CFS_OK;
   }
+  if (!strcmp(key, "multi_graph") && (value == 0 || value == 1)) {
+    g_options.multi_graph = (int)value;
+    return CFS_OK;
+  }
   if (!strcmp(key, "multi_zero_copy") && (value == 0 || value == 1)) {
     g_options.multi_zero_copy = (int)value;
     return CFS_OK;

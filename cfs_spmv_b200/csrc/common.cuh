@@ -100,6 +100,7 @@ struct Options {
   int rechunk_pct = 130; // ... as a percentage of the mean row length
   int rechunk = 1;     // ragged matrices: virtual rows of ~1.3 x the mean row length
   int tile6 = 1;      // variant 6 where it applies (bounded column windows)
+  int multi_graph = 1; // ... and replays the step of all devices as one graph
   int multi_zero_copy = 1; // cfs_cuda_multi_spmv works on managed vectors in place
   int slot_banks = 1; // variant 6: bank-aware slot assignment (tune time)
   int deterministic = 0; // y bitwise reproducible: integer reductions (det.cu)
