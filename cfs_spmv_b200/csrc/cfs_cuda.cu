@@ -339,9 +339,14 @@ static bool bind_for_alloc() {
 
 void *cfs_cuda_host_alloc_kind(size_t bytes, int kind) {
   void *p = nullptr;
-  if (kind == CFS_ALLOC_DEFAULT)
-    kind = default_alloc_kind();
   const size_t want = bytes ? bytes : 64;
+  if (kind == CFS_ALLOC_DEFAULT) {
+    kind = default_alloc_kind();
+    // small buffers gain nothing from living in HBM (a 64 KB vector is copied
+    // in 2 us) and unified allocations come in 2 MB steps of address space
+    if (kind == CFS_ALLOC_MANAGED && want < (64u << 10))
+      kind = CFS_ALLOC_PLAIN;
+  }
   if (kind != CFS_ALLOC_PLAIN && bind_for_alloc()) {
     if (kind == CFS_ALLOC_MANAGED) {
       if (cudaMallocManaged(&p, want, cudaMemAttachGlobal) == cudaSuccess) {

@@ -112,7 +112,8 @@ int cfs_cuda_set_option(const char *key, long long value);
  *                      for arrays that are uploaded once (the CSR of the host
  *                      loader)
  *   CFS_ALLOC_DEFAULT  the environment's CFS_GPU_ALLOC=managed|pinned|plain, else
- *                      managed; plain when no GPU is visible
+ *                      managed (buffers below 64 KB: plain); plain when no GPU
+ *                      is visible
  * cfs_cuda_host_alloc(bytes) = cfs_cuda_host_alloc_kind(bytes, CFS_ALLOC_DEFAULT).
  * Returns NULL on failure (the C++ wrapper prints and exit(1)s like the
  * reference). cfs_cuda_host_free takes any of them (and, like the reference's
