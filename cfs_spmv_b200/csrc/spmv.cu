@@ -466,8 +466,13 @@ int launch_sym_typed(const cfs_matrix_s *m, void *y_ext, const void *x_ext,
                      void *y_lower_base, cudaStream_t s, long long s0,
                      long long s1, double *dot, Extras ex) {
   // A shard with a fused halo: only its first slices reach below row_begin, the
-  // rest runs the plain instantiation (no per-column test against row_begin)
-  if (y_lower_base && !dot && m->halo_slice_end < s1) {
+  // rest runs the plain instantiation (no per-column test against row_begin).
+  // Only where that test sits in the inner loop -- the tile kernel of banded
+  // matrices (4-GPU step 0.45 -> 0.41 ms); in the register kernel it is one
+  // warp-uniform compare per chain, and two launches in a row cost more there
+  // (27-pt, 8 GPUs: step minus kernel 24 -> 38 us with the split).
+  if (y_lower_base && !dot && m->halo_slice_end < s1 && m->nt6 > 0 &&
+      g_options.tile6) {
     const long long hs = m->halo_slice_end > s0 ? m->halo_slice_end : s0;
     if (hs > s0)
       CFS_TRY(launch_sym_typed<T>(m, y_ext, x_ext, y_lower_base, s, s0, hs, dot,
