@@ -383,6 +383,15 @@ def cpu_baseline_and_parity(args, y_gpu):
             os.remove(y_path)
 
 
+def info_rows_total(op, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([op.e - op.b], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t)
+    return int(t.item())
+
+
 def multi_gpu_parity(rank, world):
     """N>1: the multi-GPU step on a small sharded matrix, assembled on rank 0
     and checked against the CPU oracle (the C restatement, pinned bitwise to
@@ -550,7 +559,7 @@ def main():
     # the constant-coefficient matrix beside the headline (N=1 lap27 distinct)
     compressed = None
     if world == 1 and args.workload == "lap27" and args.values == "distinct":
-        del op
+        op = None
         torch.cuda.empty_cache()
         nx, ny, nz = grid_for(1)
         op2 = ShardedSpMV(capi.GenSpec.laplacian(27, nx, ny, nz, 0), 0, 1,
@@ -575,9 +584,33 @@ def main():
         del op2
         torch.cuda.empty_cache()
 
+    # a size-independent property at the FULL size of the N-GPU workload: with
+    # per-edge coefficients every row of A sums to exactly 1/16 (diagonal =
+    # 1/16 + sum |a|, off-diagonals -a), so A*1 = 1/16 up to the rounding of a
+    # 27-term sum -- through the same exchange the timed steps used
+    full_size_property = None
+    if (world > 1 and args.workload == "lap27" and args.values == "distinct"
+            and op is not None):
+        x_keep = op.x_ext.clone()
+        op.x_ext.fill_(1.0)
+        barrier()
+        op.step(x_changed=True)
+        barrier()
+        dev = (op.y_owned() - 0.0625).abs().max().reshape(1)
+        dist.all_reduce(dev, op=dist.ReduceOp.MAX)
+        op.x_ext.copy_(x_keep)
+        barrier()
+        full_size_property = {
+            "property": "A*1 == 1/16 in every row (per-edge coefficients: "
+                        "diagonal = 1/16 + sum |a|), all %d rows, through the "
+                        "multi-GPU step" % info_rows_total(op, world),
+            "max_abs_deviation": float(dev.item()),
+            "tolerance": 1e-13, "ok": bool(dev.item() <= 1e-13)}
     parity = None
     if world > 1:
         parity = multi_gpu_parity(rank, world)
+        if parity is not None and full_size_property is not None:
+            parity["full_size_property"] = full_size_property
 
     if rank == 0:
         peak, peak_src = measured_peak()
