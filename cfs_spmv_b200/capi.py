@@ -37,7 +37,7 @@ DECLARED_SYMBOLS = (
     "cfs_cuda_matrix_tune", "cfs_cuda_matrix_destroy", "cfs_cuda_matrix_info",
     "cfs_cuda_matrix_set_hybrid",
     "cfs_cuda_spmv", "cfs_cuda_spmv_async", "cfs_cuda_spmv_halo_async",
-    "cfs_cuda_spmv_shard_async",
+    "cfs_cuda_spmv_shard_async", "cfs_cuda_spmv_shard_part_async",
     "cfs_cuda_spmv_timed", "cfs_cuda_cg_solve",
     "cfs_cuda_spmv_halo_dot_async", "cfs_cuda_cg_update_xr",
     "cfs_cuda_cg_update_p",
@@ -217,6 +217,8 @@ def lib():
     L.cfs_cuda_spmv_halo_async.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
     L.cfs_cuda_spmv_shard_async.argtypes = [vp, vp, vp, vp, vp, vp,
                                             ctypes.c_int, vp]
+    L.cfs_cuda_spmv_shard_part_async.argtypes = [vp, vp, vp, vp, vp, vp,
+                                                 ctypes.c_int, vp]
     L.cfs_cuda_spmv_timed.argtypes = [vp, vp, vp, vp, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_float),
                                       ctypes.POINTER(ctypes.c_float)]
@@ -383,6 +385,14 @@ class Matrix:
         check(lib().cfs_cuda_spmv_shard_async(
             self._h, _ptr(y_dev), _ptr(x_dev), y_lower_base, x_lower_base,
             _ptr(y_clear), int(y_is_zero), stream))
+
+    def spmv_shard_part_async(self, y_dev, x_dev, y_lower_base, x_lower_base,
+                              y_clear, part, stream=0):
+        """part 1: the slices that reach below row_begin (remote x / y);
+        part 2: all the others"""
+        check(lib().cfs_cuda_spmv_shard_part_async(
+            self._h, _ptr(y_dev), _ptr(x_dev), y_lower_base, x_lower_base,
+            _ptr(y_clear), part, stream))
 
     def cg_solve(self, x, b, max_iters, rel_tol, want_history=False):
         """A x = b by conjugate gradients on the device (cfs_cuda_cg_solve).

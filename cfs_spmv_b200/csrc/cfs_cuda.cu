@@ -852,6 +852,32 @@ int cfs_cuda_spmv_shard_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                          x_lower_base, y_clear);
 }
 
+int cfs_cuda_spmv_shard_part_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                                   void *y_lower_base, const void *x_lower_base,
+                                   void *y_clear, int part, void *stream) {
+  if (!m || !y_dev || !x_dev || part < 1 || part > 2)
+    return CFS_ERR_INVALID;
+  if (!m->tuned || !m->symmetric) {
+    set_error("cfs_cuda_spmv_shard_part_async: needs a tuned symmetric matrix");
+    return CFS_ERR_STATE;
+  }
+  const long long hs = m->halo_slice_end < m->nslices ? m->halo_slice_end
+                                                      : m->nslices;
+  if (part == 1) { // the slices that reach below row_begin
+    if (hs == 0 || !y_lower_base)
+      return CFS_OK;
+    return launch_sym_spmv(m, y_dev, x_dev, (cudaStream_t)stream, nullptr,
+                           nullptr, y_lower_base, true, 0, hs, nullptr,
+                           x_lower_base, y_clear);
+  }
+  const long long from = y_lower_base ? hs : 0; // no halo: everything is interior
+  if (from >= m->nslices)
+    return CFS_OK;
+  return launch_sym_spmv(m, y_dev, x_dev, (cudaStream_t)stream, nullptr,
+                         nullptr, nullptr, true, from, m->nslices, nullptr,
+                         nullptr, y_clear);
+}
+
 // Host vectors in, host vectors out: H2D of x, the kernel and D2H of y overlap
 // chunk by chunk (see cfs_matrix_s::Chunk). Three streams, events between them.
 // enqueue_pipeline issues one whole step; with pinned vectors the step is

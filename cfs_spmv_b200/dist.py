@@ -159,7 +159,17 @@ class P2PHalo:
             peer_x = self.hx.get_buffer(rank - 1, (max_len,), dtype)
             self.x_peer = peer_x[self.h - ph:self.b - ph]
         self.bytes_per_step = 2 * self.nhalo * item
+        # the rows the GPU above reduces into: [its halo_begin, my row_end)
+        self.band = None
+        if rank + 1 < self.world and ranges[rank + 1][0] < ranges[rank + 1][1]:
+            lo = max(ranges[rank + 1][0], self.b) - self.h
+            self.band = (lo, self.e - self.h)
         self.sync = os.environ.get("CFS_GPU_HALO_SYNC", "barrier")
+        self.overlap = os.environ.get("CFS_GPU_HALO_OVERLAP", "1") != "0"
+        self.side = torch.cuda.Stream(device=device)
+        self.ev_part1 = None
+        self.ev_main = None
+        self.dirty = False
         self.t = 0
         self.reset()
 
@@ -175,6 +185,7 @@ class P2PHalo:
 
     def reset(self):
         """both result vectors clear on every rank"""
+        self.join()
         self.y_sym.zero_()
         self.t = 0
         self.hy.barrier()
@@ -209,15 +220,73 @@ class P2PHalo:
             self.hy.wait_signal(self.rank + 1, 1, self._TIMEOUT_MS)
 
     def step(self, matrix, stream, x_changed=False):
-        if x_changed:
-            self.hy.barrier()          # x below is final
+        if x_changed or not self.overlap:
+            if x_changed:
+                self.join()
+                self.hy.barrier()      # x below is final
+            k = self.t % 2
+            matrix.spmv_shard_async(self.y_bufs[k], self.x_ext,
+                                    self.y_lower_bases[k], self.x_lower_base,
+                                    self.y_bufs[1 - k], True, stream)
+            self.hy.barrier()          # reductions landed, other vector clear
+            self.t += 1
+            return self.y_bufs[k]
+        return self._step_overlapped(matrix)
+
+    # The barrier off the critical path (CFS_GPU_HALO_OVERLAP=0 switches it
+    # off). Only the leading slices of a shard touch the GPU below (part 1:
+    # 0.1-2 % of them); all the others (part 2) need nothing from anybody else.
+    #   main stream:  ... part2(t) ................. part2(t+1) ...
+    #   side stream:  barrier(t-1) -> part1(t) -> [part2(t) done] barrier(t) -> part1(t+1)
+    # part 1 of step t runs behind barrier t-1 (every GPU has finished step
+    # t-1: the vector it reduces into is clear, x below is final) and next to
+    # part 2 of the same step; barrier t waits for both parts; part 2 of step
+    # t+1 only waits for part 1 of step t (rows that part cleared / reduced).
+    # One more thing follows from not waiting: part 2 of step t clears the OTHER
+    # vector while the GPU above may still be reducing its step t-1 halo into
+    # the top rows of that vector (the band), so the band is cleared once more
+    # behind barrier t-1, when those reductions have certainly landed.
+    def _step_overlapped(self, matrix):
+        import torch
+        main = torch.cuda.current_stream()
+        side = self.side
         k = self.t % 2
-        matrix.spmv_shard_async(self.y_bufs[k], self.x_ext,
-                                self.y_lower_bases[k], self.x_lower_base,
-                                self.y_bufs[1 - k], True, stream)
-        self.hy.barrier()              # reductions landed, other vector clear
+        if self.ev_part1 is not None:
+            main.wait_event(self.ev_part1)        # part1(t-1) has finished
+        matrix.spmv_shard_part_async(self.y_bufs[k], self.x_ext,
+                                     self.y_lower_bases[k], self.x_lower_base,
+                                     self.y_bufs[1 - k], 2, main.cuda_stream)
+        ev_main = torch.cuda.Event()
+        ev_main.record(main)
+        if self.ev_main is not None:
+            side.wait_event(self.ev_main)         # part2(t-1): before barrier(t-1)
+        else:
+            side.wait_stream(main)                # first step: set-up is done
+        with torch.cuda.stream(side):
+            if self.band is not None:             # behind barrier(t-1)
+                self.y_bufs[1 - k][self.band[0]:self.band[1]].zero_()
+            matrix.spmv_shard_part_async(self.y_bufs[k], self.x_ext,
+                                         self.y_lower_bases[k],
+                                         self.x_lower_base, self.y_bufs[1 - k],
+                                         1, side.cuda_stream)
+            self.ev_part1 = torch.cuda.Event()
+            self.ev_part1.record(side)
+            side.wait_event(ev_main)              # part2(t) has finished
+            self.hy.barrier()                     # barrier(t)
+        self.ev_main = ev_main
+        self.dirty = True
         self.t += 1
         return self.y_bufs[k]
+
+    def join(self):
+        """the main stream waits for everything the side stream has been given
+        (a consumer of y, a step that is not overlapped)"""
+        import torch
+        if getattr(self, "dirty", False):
+            torch.cuda.current_stream().wait_stream(self.side)
+            self.dirty = False
+            self.ev_part1 = None
+            self.ev_main = None
 
 
 class ShardedSpMV:
@@ -301,9 +370,18 @@ class ShardedSpMV:
                 "fused over NVLink peer memory: ONE kernel per step reads its x "
                 "halo from the GPU below, reduces its y halo contributions "
                 "straight into that GPU's y (RED.sys) and clears the other of "
-                "two result vectors; ONE device barrier per step; %d bytes on "
-                "rank %d" % (self.p2p.bytes_per_step, rank))
-            self.kernels_per_step = 2  # SpMV + the symmetric-memory barrier
+                "two result vectors; ONE device barrier per step%s; %d bytes on "
+                "rank %d" % (", off the critical path: the slices that touch "
+                             "the GPU below run on a side stream behind the "
+                             "previous step's barrier, next to all the others"
+                             if self.p2p.overlap else "",
+                             self.p2p.bytes_per_step, rank))
+            # SpMV (interior + halo part when overlapped) + the symmetric-memory
+            # barrier (+ the band clear)
+            self.kernels_per_step = 2 + (
+                (1 if self.p2p.nhalo > 0 else 0) +
+                (1 if self.p2p.band is not None else 0)
+                if self.p2p.overlap else 0)
         else:
             self.exchange_desc = (
                 "NCCL P2P per step: x halo down-up, y halo strip add; "
@@ -396,6 +474,7 @@ class ShardedSpMV:
         no halo exchange and no barrier -- a shard reduces its halo
         contributions into the halo part of its own vector"""
         import torch
+        self.sync()
         s = torch.cuda.current_stream()
         bufs = self.y_bufs
         if self.p2p is not None:  # private vectors: nothing of a neighbour's
@@ -421,7 +500,14 @@ class ShardedSpMV:
             self.t = 0
         return e0.elapsed_time(e1) / iters
 
+    def sync(self):
+        """the current stream waits for whatever the overlapped step left on
+        its side stream (the last barrier and halo part)"""
+        if self.p2p is not None:
+            self.p2p.join()
+
     def y_owned(self):
+        self.sync()
         return self.y_ext[self.b - self.h:]
 
     def checksum(self):

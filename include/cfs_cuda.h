@@ -285,6 +285,19 @@ int cfs_cuda_spmv_shard_async(cfs_mat_t m, void *y_dev, const void *x_dev,
                               void *y_lower_base, const void *x_lower_base,
                               void *y_clear, int y_is_zero, void *stream);
 
+/* The two parts of that step as separate launches, for callers that overlap
+ * the synchronisation of the GPUs with the bulk of the work: part 1 = the
+ * leading slices that reference columns below row_begin (they read the x of
+ * and reduce into the y of the GPU below: y_lower_base / x_lower_base as
+ * above; nothing to do on the lowest GPU), part 2 = all other slices (no
+ * remote access; pass the same y_lower_base so that the split point is the
+ * same, it is not dereferenced). y must be clear on entry; both parts clear
+ * the rows they own in y_clear. cfs_spmv_b200/dist.py (P2PHalo.step) runs part
+ * 2 on the main stream while a side stream runs barrier -> part 1. */
+int cfs_cuda_spmv_shard_part_async(cfs_mat_t m, void *y_dev, const void *x_dev,
+                                   void *y_lower_base, const void *x_lower_base,
+                                   void *y_clear, int part, void *stream);
+
 /* ---- one process, several GPUs: replaces the role of get_num_threads
  * (src/runtime.cpp:10-21) + partition_by_nnz (csr_matrix.tpp:438-541) for the
  * GPUs of one box. The C++ layer takes this path when CFS_NUM_GPUS > 1
