@@ -188,6 +188,8 @@ def test_new_entry_points_fail_loudly_without_a_gpu():
     assert L.cfs_cuda_spmv_shard_async(None, None, None, None, None, None, 1,
                                        None) == capi.CFS_ERR_INVALID
     assert L.cfs_cuda_multi_spmv(None, None, None) == capi.CFS_ERR_INVALID
+    assert L.cfs_cuda_spmv_shard_part_async(None, None, None, None, None, None,
+                                            1, None) == capi.CFS_ERR_INVALID
     for key, val in (("deterministic", 1), ("deterministic", 0),
                      ("keep_layouts", 0), ("l2_prefetch", 1),
                      ("managed_prefetch", 1), ("spmv_variant", 7),
