@@ -12,9 +12,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+@pytest.mark.parametrize("halo", ["p2p", "p2p-bulk-synchronous", "nccl"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_spmv_matches_oracle(gpu, world, halo):
+    """p2p: fused NVLink halo with the barrier off the critical path (part
+    launches on two streams); p2p-bulk-synchronous: the same kernel and barrier
+    in one stream (CFS_GPU_HALO_OVERLAP=0); nccl: point-to-point messages"""
+    overlap = "0" if halo == "p2p-bulk-synchronous" else "1"
+    halo = "p2p" if halo.startswith("p2p") else halo
     if gpu.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     s = socket.socket()
@@ -27,7 +32,7 @@ def test_sharded_spmv_matches_oracle(gpu, world, halo):
          "--master-port", str(port),
          os.path.join(ROOT, "tests", "multi_gpu_worker.py")],
         capture_output=True, text=True, timeout=600,
-        env=dict(os.environ, CFS_GPU_HALO=halo))
+        env=dict(os.environ, CFS_GPU_HALO=halo, CFS_GPU_HALO_OVERLAP=overlap))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "FAIL" not in r.stdout
     assert r.stdout.count("err=") == 3 and r.stdout.count(" OK") >= 3
