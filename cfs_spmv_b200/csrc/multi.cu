@@ -344,6 +344,11 @@ static int zero_copy_spmv(cfs_multi_t mm, void *y, const void *x) {
   // ~30 us after the first). Captured once per (x, y) pair as ONE multi-device
   // graph it is one launch and one join; a capture that fails falls back to
   // issuing the calls directly.
+  if (moved) // the prefetches are done before anything touches the pages
+    for (int g = 0; g < G; ++g) {
+      CFS_CUDA_TRY(cudaSetDevice(mm->device[g]));
+      CFS_CUDA_TRY(cudaStreamSynchronize(mm->stream[g]));
+    }
   // (the first step of a pair is issued directly: it sets function attributes
   // and warms the pages; the second one is captured)
   const bool repeat = mm->seen_x == x && mm->seen_y == y;
